@@ -1,0 +1,224 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz by running the reference's own, unmodified hot-path
+files (through oracle/ref_shim.py) on small seeded inputs.  Run in the build container, where /root/reference
+is mounted:
+
+    python oracle/make_golden.py
+
+The fixtures pin oracle/srx_oracle.py (tests/test_oracle_vs_golden.py) and serve the `-m gpu` parity tests on
+the GPU box, where the reference tree does not exist.  Determinism: torch.set_num_threads(1) — defines the
+duplicate-index write order of the reference.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_shim  # noqa: E402
+from stable_renderer_b200 import synthetic  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+class _Ctx:
+    def __init__(self, noise, timestep):
+        self.noise = noise
+        self.denoised = noise
+        self.timestep = timestep
+        self.step_index = 0
+        self.total_steps = 20
+
+
+class _EngineData:
+    def __init__(self, id_maps, correspond_maps=None):
+        self.id_maps = id_maps
+        self.correspond_maps = correspond_maps
+
+
+def ref_step(R, ids_t, x_t, ratio, frame_indices=None, timestep=900, stop=500):
+    IDMap = R["corrmap"].IDMap
+    idm = IDMap(tensor=ids_t.clone(), frame_indices=None if frame_indices is None else list(frame_indices))
+    oc = R["corresponder"].OverlapCorresponder(step_finished_inject_ratio=ratio,
+                                               step_finished_stop_inject_timestep=stop)
+    ctx = _Ctx(x_t.clone(), timestep)
+    with ref_shim.quiet():
+        oc.step_finished(_EngineData(idm), ctx)
+        vsi = idm.create_vertex_screen_info()
+    return ctx.noise, vsi, idm.masks
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def step_cases(R):
+    cases = {
+        # name: (F, H, W, h, w, tex, frac2048, frame_indices, ratio, n_obj)
+        "step_sq64_r8": (4, 64, 64, 8, 8, 64, 0.05, None, 0.5, 1),
+        "step_sq96_r8_perm": (3, 96, 96, 12, 12, 96, 0.03, [2, 0, 1], 0.1, 1),
+        "step_sq100_nonint": (3, 100, 100, 12, 12, 64, 0.0, None, 0.35, 2),
+        "step_sq60_to_16": (2, 60, 60, 16, 16, 32, 0.1, None, 1.0, 1),
+        "step_dupframe": (3, 64, 64, 8, 8, 64, 0.0, [0, 1, 1], 0.5, 1),
+    }
+    for name, (F, H, W, h, w, tex, f2048, fidx, ratio, n_obj) in cases.items():
+        ids = synthetic.make_ids(F, H, W, tex_h=tex, tex_w=tex, n_obj=n_obj, frac_2048=f2048, seed=11)
+        B = F if fidx is None else max(fidx) + 1
+        x = synthetic.make_latents(B, 4, h, w, seed=3)
+        out, vsi, masks = ref_step(R, ids, x, ratio, fidx)
+        save(name, ids=ids.numpy(), x=x.numpy(), ratio=np.float64(ratio),
+             frame_indices=np.array(list(range(F)) if fidx is None else fidx, dtype=np.int64),
+             out=out.numpy(), vsi=vsi.numpy(), masks=masks.numpy())
+    # gate: timestep below stop -> untouched
+    ids = synthetic.make_ids(2, 64, 64, tex_h=64, tex_w=64, seed=11)
+    x = synthetic.make_latents(2, 4, 8, 8, seed=3)
+    out, vsi, _ = ref_step(R, ids, x, 0.5, None, timestep=100, stop=500)
+    save("step_gate_off", ids=ids.numpy(), x=x.numpy(), ratio=np.float64(0.5), out=out.numpy(),
+         timestep=np.float64(100), stop=np.float64(500))
+    # half precision inputs (tolerance cases, corresponder.py:317-318 / math_utils.py:42-51)
+    ids = synthetic.make_ids(4, 64, 64, tex_h=64, tex_w=64, seed=11)
+    for dt, tag in ((torch.float16, "f16"), (torch.bfloat16, "bf16")):
+        x = synthetic.make_latents(4, 4, 8, 8, seed=5, dtype=dt)
+        out, _, _ = ref_step(R, ids, x, 0.5)
+        save(f"step_half_{tag}", ids=ids.numpy(), x=x.float().numpy(), ratio=np.float64(0.5),
+             out=out.float().numpy())
+    # crop of the bundled real data (resources/example-sphere-and-object-views/sphere/id, int16, legacy layout)
+    d = os.path.join(ref_shim.REFERENCE_ROOT, "resources", "example-sphere-and-object-views", "sphere", "id")
+    names = sorted(os.listdir(d), key=lambda n: int(n.split("_")[1].split(".")[0]))[:4]
+    crop = np.stack([np.load(os.path.join(d, n))[160:288, 192:320] for n in names])
+    ids = torch.from_numpy(crop.copy())
+    x = synthetic.make_latents(4, 4, 16, 16, seed=0)
+    out, vsi, _ = ref_step(R, ids, x, 0.5)
+    save("step_sphere_crop_int16", ids=crop, x=x.numpy(), ratio=np.float64(0.5), out=out.numpy(),
+         n_entries=np.int64(vsi.shape[0]))
+
+
+def bake_cases(R):
+    CorrespondMap = R["corrmap"].CorrespondMap
+    IDMap = R["corrmap"].IDMap
+    F, H, W, tex, k = 4, 64, 64, 32, 2
+    ids = synthetic.make_ids(F, H, W, tex_h=tex, tex_w=tex, k=k, frac_2048=0.05, seed=21)
+    colors = synthetic.make_colors(F, H, W, 3, seed=9)
+    masks = IDMap(tensor=ids.clone()).masks  # 1 = no id
+    for mode in ("first", "replace", "first_avg", "replace_avg"):
+        cm = CorrespondMap(name="g", k=k, height=tex, width=tex, channel_count=4)
+        with ref_shim.quiet():
+            cm.update(colors.clone(), ids.clone(), spriteID=1, materialID=0, mode=mode, masks=masks.clone(),
+                      inverse_masks=True, ignore_obj_mat_id=True)
+        save(f"bake_{mode}_masked", ids=ids.numpy(), colors=colors.numpy(), masks=masks.numpy(),
+             values=cm._values.numpy(), writtens=cm._writtens.numpy(), k=np.int64(k), tex=np.int64(tex))
+    # two successive updates in 'first' mode (second call must not overwrite), rgba input, no 2048 pixels
+    ids2 = synthetic.make_ids(F, H, W, tex_h=tex, tex_w=tex, k=k, n_obj=2, seed=22)
+    col4 = synthetic.make_colors(F, H, W, 4, seed=10)
+    cm = CorrespondMap(name="g", k=k, height=tex, width=tex, channel_count=4)
+    with ref_shim.quiet():
+        cm.update(col4[:2].clone(), ids2[:2].clone(), spriteID=2, materialID=0, mode="first")
+        cm.update(col4[2:].clone(), ids2[2:].clone(), spriteID=2, materialID=0, mode="first")
+    save("bake_first_sprite2_two_calls", ids=ids2.numpy(), colors=col4.numpy(), values=cm._values.numpy(),
+         writtens=cm._writtens.numpy(), k=np.int64(k), tex=np.int64(tex), spriteID=np.int64(2))
+    # through DefaultCorresponder.finished (corresponder.py:130-155)
+    cm = CorrespondMap(name="g", k=k, height=tex, width=tex, channel_count=3)
+    dc = R["corresponder"].DefaultCorresponder(update_corrmap_mode="replace", ignore_obj_mat_id_when_update=True)
+    ed = _EngineData(IDMap(tensor=ids.clone()), {(1, 0): cm})
+    with ref_shim.quiet():
+        dc.finished(ed, colors.clone())
+    save("bake_finished_replace_c3", ids=ids.numpy(), colors=colors.numpy(), values=cm._values.numpy(),
+         writtens=cm._writtens.numpy(), k=np.int64(k), tex=np.int64(tex))
+
+
+def legacy_cases(R):
+    CorrespondenceMap = R["correspondence_map"].CorrespondenceMap
+    ov = R["overlap"]
+    Scheduler = R["overlap_scheduler"].Scheduler
+    factory = R["algorithms"].overlap_algorithm_factory
+    T, H, W, h, w = 4, 32, 32, 4, 4
+    ids = synthetic.make_ids(T, H, W, tex_h=16, tex_w=16, seed=31, legacy_layout=True, dtype=torch.int16)
+    with tempfile.TemporaryDirectory() as td:
+        iddir = os.path.join(td, "id")
+        os.makedirs(iddir)
+        for f in range(T):
+            np.save(os.path.join(iddir, f"id_{f}.npy"), ids[f].numpy())
+        with ref_shim.quiet():
+            cmap = CorrespondenceMap.FromExisting(iddir, enable_cache=False)
+    keys = np.array(list(cmap.Map.keys()), dtype=np.int64)
+    lens = np.array([len(v) for v in cmap.Map.values()], dtype=np.int64)
+    flat = np.array([(p[0], p[1], f) for v in cmap.Map.values() for (p, f) in v], dtype=np.int64)
+    save("legacy_corrmap", ids=ids.numpy(), keys=keys, lens=lens, traces=flat,
+         size=np.array(cmap.size, dtype=np.int64))
+    merged = CorrespondenceMap(dict(cmap.Map), cmap.width, cmap.height, cmap.num_frames)
+    with ref_shim.quiet():
+        merged.merge_nearby(4)
+    mkeys = np.array(list(merged.Map.keys()), dtype=np.int64)
+    mlens = np.array([len(v) for v in merged.Map.values()], dtype=np.int64)
+    mflat = np.array([(p[0], p[1], f) for v in merged.Map.values() for (p, f) in v], dtype=np.int64)
+    save("legacy_corrmap_merge4", keys=mkeys, lens=mlens, traces=mflat)
+
+    torch.manual_seed(0)
+    frames = [torch.randn(1, 4, h, w, dtype=torch.float64) for _ in range(T)]
+    vn = torch.rand(T, H, W, 1, dtype=torch.float64)
+    alpha_s = Scheduler(interpolate_begin=0.7, interpolate_end=0.7, interpolate_type="constant")
+    res = {}
+    for radius in (0, 1):
+        rad_s = Scheduler(interpolate_begin=float(radius), interpolate_end=float(radius), interpolate_type="constant")
+        for strat in ("average", "frame_distance", "pixel_distance", "perpendicular_view_normal"):
+            for cm_name, cm in (("full", cmap), ("merge4", merged)):
+                o = ov.ResizeOverlap(alpha_s, rad_s, factory(strat), verbose=False)
+                with ref_shim.quiet():
+                    outs = o([f.clone() for f in frames], cm, step=0, timestep=500, view_normal_map=vn)
+                res[f"out_{strat}_r{radius}_{cm_name}"] = torch.stack(outs).numpy()
+    save("legacy_resize_overlap", ids=ids.numpy(), frames=torch.stack(frames).numpy(), view_normal=vn.numpy(),
+         alpha=np.float64(0.7), **res)
+
+    # scheduler table (overlap_scheduler.py:89-107 / utils.py:24-53); cosine only works for tensor timesteps
+    rows = []
+    for itype in ("constant", "linear", "exponential", "cosine"):
+        for power in (1.0, 2.0):
+            s = Scheduler(every_step=2, start_step=2, end_step=40, start_timestep=100, end_timestep=900,
+                          interpolate_begin=0.9, interpolate_end=0.2, power=power, interpolate_type=itype,
+                          no_interpolate_return=0.05)
+            for step in (0, 2, 3, 10, 40, 42):
+                for ts in (50, 100, 500, 900, 950):
+                    tsv = torch.tensor(float(ts), dtype=torch.float64) if itype == "cosine" else ts
+                    v = s(step, tsv)
+                    rows.append((("constant", "linear", "exponential", "cosine").index(itype), power, step, ts, float(v)))
+    save("legacy_scheduler", table=np.array(rows, dtype=np.float64))
+
+
+def group_cases(R):
+    mu = R["math_utils"]
+    t = torch.tensor([[2, 1, 4], [2, 9, 12], [6, 4, 4], [7, 3, 99], [8, 1, 3]])
+    a0 = mu.tensor_group_by_then_average(t, index_column=0, value_columns=[1, 2])[0]
+    a1, u1 = mu.tensor_group_by_then_average(t, index_column=1, value_columns=[0], return_unique=True)
+    g = torch.Generator().manual_seed(1)
+    big = torch.cat([torch.randn(5000, 4, generator=g), torch.randint(0, 37, (5000, 1), generator=g).float()], dim=1)
+    b, ub = mu.tensor_group_by_then_average(big, index_column=-1, value_columns=[0, 1, 2, 3], return_unique=True)
+    c = torch.randn(3, 4, 8, 8, generator=g)
+    s = torch.randn(3, 4, 8, 8, generator=g) * 2 + 1
+    ad = mu.adaptive_instance_normalization(c, s)
+    save("group_by_average", t=t.numpy(), a0=a0.numpy(), a1=a1.numpy(), u1=u1.numpy(), big=big.numpy(),
+         b=b.numpy(), ub=ub.numpy(), content=c.numpy(), style=s.numpy(), adain=ad.numpy())
+
+
+def main():
+    if not ref_shim.available():
+        raise SystemExit("reference tree not mounted; fixtures can only be regenerated in the build container")
+    torch.set_num_threads(1)
+    R = ref_shim.load_reference()
+    group_cases(R)
+    step_cases(R)
+    bake_cases(R)
+    legacy_cases(R)
+
+
+if __name__ == "__main__":
+    main()
