@@ -1,0 +1,228 @@
+/* srx.h — C ABI of libsrx.so: B200 (sm_100a) kernels for Stable-Renderer's correspondence-map latent overlap step
+ * and UV-texture bake.
+ *
+ * The reference (92MING/Stable-Renderer) has no FFI for this path: it is pure Python calling torch ops
+ * (SURVEY.md §8b).  Each entry point below therefore names the reference *Python* interface whose arithmetic it
+ * replaces (paths relative to the reference root).  The Python wrappers in stable-renderer_b200/ keep those
+ * signatures and call these functions through ctypes; INTEGRATION.md shows the binding a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative srx_status; srx_last_error() returns the message of the
+ *     last failure on the calling thread.  No exceptions cross the boundary.
+ *   - all `*_dev` / `void*` data pointers are DEVICE pointers owned by the caller (torch tensors); the library
+ *     never frees them.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - nothing synchronises the host unless stated ("syncs").
+ *   - handles are opaque and destroyed explicitly.
+ */
+#ifndef SRX_H_
+#define SRX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRX_VERSION 100 /* 0.1.0 */
+
+typedef enum srx_status {
+    SRX_OK = 0,
+    SRX_ERR_INVALID = -1,     /* bad argument (maps to ValueError) */
+    SRX_ERR_INDEX = -2,       /* an entry addresses a latent cell / texel out of range (maps to IndexError) */
+    SRX_ERR_CUDA = -3,        /* CUDA runtime error */
+    SRX_ERR_UNSUPPORTED = -4, /* valid request that this build does not implement */
+    SRX_ERR_KEY_RANGE = -5    /* key outside the dense slot table */
+} srx_status;
+
+typedef enum srx_dtype {
+    SRX_F32 = 0, SRX_F16 = 1, SRX_BF16 = 2, /* latents / colours */
+    SRX_I32 = 10, SRX_I16 = 11,             /* id buffers (RGBA_32I attachment, or the int16 .npy dumps) */
+    SRX_U8 = 20
+} srx_dtype;
+
+/* What identifies "the same surface point" across frames. */
+typedef enum srx_key_mode {
+    /* current generation: float32(vertexID) only — corresponder.py:331-334 */
+    SRX_KEY_VERTEX = 0,
+    /* legacy generation: the whole id 4-tuple, optionally merged (texX//d, texY//d) —
+       legacy_codes/stable_rendering_algo/data_classes/correspondence_map.py:153-168, 276-286 */
+    SRX_KEY_TUPLE = 1
+} srx_key_mode;
+
+typedef enum srx_strategy { /* legacy_codes/stable_rendering_algo/overlap/algorithms.py:34-133 */
+    SRX_STRATEGY_AVERAGE = 0,
+    SRX_STRATEGY_FRAME_DISTANCE = 1,
+    SRX_STRATEGY_PIXEL_DISTANCE = 2,
+    SRX_STRATEGY_VIEW_NORMAL = 3
+} srx_strategy;
+
+typedef enum srx_accum_mode {
+    SRX_ACCUM_FAST = 0,         /* float32 vector atomics (order not fixed; within 1e-5 of the reference) */
+    SRX_ACCUM_DETERMINISTIC = 1 /* Q31.32 fixed-point int64 atomics: order independent, bit reproducible */
+} srx_accum_mode;
+
+int srx_version(void);
+const char *srx_last_error(void);
+/* number of SMs of the current device (grid sizing is a multiple of this) */
+int srx_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Keying plan  — replaces IDMap.create_vertex_screen_info (source/engine/static/corrmap.py:220-280) and the
+ * coordinate step of OverlapCorresponder.step_finished (source/common_utils/stable_render_utils/corresponder.py:310-314)
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct srx_plan srx_plan;
+
+typedef struct srx_plan_desc {
+    int id_dtype;            /* SRX_I32 | SRX_I16 */
+    int frames;              /* F: id frames */
+    int height, width;       /* H, W of the id buffers */
+    int batch;               /* B: latent frames */
+    int channels;            /* C: latent channels (4 for SD1.5 / SDXL) */
+    int lat_h, lat_w;        /* h, w of the latents */
+    int key_mode;            /* srx_key_mode */
+    int merge_len;           /* SRX_KEY_TUPLE only: merge_nearby distance, 0/1 = off */
+    int accum_mode;          /* srx_accum_mode */
+    int64_t key_capacity;    /* dense slot count; 0 = derive with a scan of the ids (syncs) */
+    const int32_t *frame_map;/* HOST array [F]: value used as batch index of each id frame (corrmap.py:251-253,
+                                corresponder.py:314); NULL = identity.  Negative values wrap like torch indexing. */
+} srx_plan_desc;
+
+typedef struct srx_plan_info {
+    int64_t n_valid;         /* entries (valid pixels); -1 when no scan ran */
+    int64_t key_min, key_max;/* over valid pixels; meaningful when a scan ran */
+    int64_t key_capacity;    /* slots in the dense accumulator */
+    int64_t workspace_bytes; /* device bytes the caller must bind with srx_plan_bind_workspace */
+    int64_t accum_offset;    /* byte offset / size of the accumulator block inside the workspace ... */
+    int64_t accum_bytes;     /* ... i.e. the buffer a multi-GPU caller all-reduces between reduce and gather */
+    int accum_dtype;         /* SRX_F32 (fast) — int64 in deterministic mode is reported as -64 */
+    int fast_path;           /* 1 when the 8x8-pixels-per-cell warp kernel applies */
+} srx_plan_info;
+
+/* Builds the plan for one batch of id buffers.  `ids_dev` may be NULL when key_capacity > 0 (ids are then given to
+ * each call).  Syncs only when key_capacity == 0 (scan).  Errors: SRX_ERR_INDEX when a valid pixel maps outside
+ * the latent (the reference raises IndexError at corresponder.py:324-329). */
+int srx_plan_create(srx_plan **out, const srx_plan_desc *desc, const void *ids_dev, void *stream);
+int srx_plan_get_info(const srx_plan *plan, srx_plan_info *info);
+int srx_plan_bind_workspace(srx_plan *plan, void *workspace_dev, int64_t bytes, void *stream);
+int srx_plan_destroy(srx_plan *plan);
+/* Lazily reported device-side failures of earlier launches (key out of the slot table, cell out of range).
+ * Syncs the stream. */
+int srx_plan_check(srx_plan *plan, void *stream);
+
+/* [N,7] float32 rows (sprite, material, map_index, vertexID, x/H, y/W, frame value) in (frame,y,x) order —
+ * bit-identical to IDMap.create_vertex_screen_info (corrmap.py:220-280).  `out_dev` must hold F*H*W*7 floats
+ * (worst case); *n_rows receives N.  Syncs. */
+int srx_vertex_screen_info(const void *ids_dev, int id_dtype, int frames, int height, int width,
+                           const int32_t *frame_values_host, float *out_dev, int64_t *n_rows, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Overlap step — replaces OverlapCorresponder.step_finished (corresponder.py:298-376):
+ * gather, tensor_group_by_then_average (source/common_utils/math_utils.py:86-161), blend, duplicate-index
+ * write-back (last entry wins) and adaptive_instance_normalization (math_utils.py:55-80); in place on `x_dev`.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct srx_step_args {
+    void *x_dev;             /* latents [B,C,h,w], contiguous, updated in place */
+    int x_dtype;             /* SRX_F32 | SRX_F16 | SRX_BF16 */
+    const void *ids_dev;     /* id buffers [F,H,W,4] of this step (streaming regime); NULL = use the plan's cached slots */
+    float ratio;             /* step_finished_inject_ratio (corresponder.py:180,351-352) */
+    int adain;               /* 1 = reference behaviour (re-standardise the original latents); 0 = write the blend */
+    int cache_slots;         /* 1 = also record the per-pixel slot map so later steps can pass ids_dev = NULL */
+} srx_step_args;
+
+/* reduce + gather on one GPU */
+int srx_overlap_step(srx_plan *plan, const srx_step_args *args, void *stream);
+/* split form for frame-sharded multi-GPU runs: reduce into the plan's accumulator, all-reduce that block with NCCL,
+ * then gather */
+int srx_accum_reduce(srx_plan *plan, const srx_step_args *args, void *stream);
+int srx_accum_finalize_gather(srx_plan *plan, const srx_step_args *args, void *stream);
+
+/* tensor_group_by_then_average on explicit columns (math_utils.py:86-161): values [N,C] float32 and float32 keys [N];
+ * writes the per-row group mean [N,C].  Keys must be non-negative integers < key_capacity. Workspace: key_capacity*(C+1) floats. */
+int srx_group_by_then_average(const float *values_dev, const float *keys_dev, int64_t n, int channels,
+                              float *out_dev, float *workspace_dev, int64_t key_capacity, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Legacy overlap — replaces ResizeOverlap.__call__ / Overlap.__call__ with kernel_radius 0
+ * (legacy_codes/stable_rendering_algo/overlap/overlap.py:83-152,180-222) for the four OverlapAlgorithm strategies
+ * (overlap/algorithms.py:34-118).  Latents [T,B,C,h,w] (B folded into channels), ids [T,H,W,4] keyed by the whole id
+ * 4-tuple like CorrespondenceMap.FromExisting (legacy data_classes/correspondence_map.py:145-170).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct srx_legacy_desc {
+    int id_dtype;              /* SRX_I32 | SRX_I16 */
+    int frames, height, width; /* T, H, W of the id buffers (= CorrespondenceMap.num_frames / .size) */
+    int channels;              /* B*C of one frame's latent [B,C,h,w] */
+    int lat_h, lat_w;          /* h, w; equal to H, W for Overlap.__call__, smaller for ResizeOverlap.__call__ */
+    int merge_len;             /* merge_nearby distance (correspondence_map.py:276-286); 0/1 = off */
+    int strategy;              /* srx_strategy */
+} srx_legacy_desc;
+
+typedef struct srx_legacy_args {
+    void *x_dev;               /* [T, B*C, h, w] updated in place */
+    int x_dtype;               /* SRX_F32 | SRX_F16 | SRX_BF16 */
+    const void *ids_dev;       /* [T,H,W,4] */
+    float alpha;               /* alpha scheduler value (overlap.py:100,145) */
+    const float *view_normal_dev; /* [T,H,W] float32 for SRX_STRATEGY_VIEW_NORMAL (utils.py:56-102), else NULL */
+    void *workspace_dev;       /* srx_legacy_workspace_bytes() bytes */
+    int64_t workspace_bytes;
+} srx_legacy_args;
+int64_t srx_legacy_workspace_bytes(const srx_legacy_desc *desc);
+/* Errors (after a sync) with SRX_ERR_KEY_RANGE when an id component does not fit the packed 64-bit key. */
+int srx_legacy_overlap(const srx_legacy_desc *desc, const srx_legacy_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Bake — replaces CorrespondMap.update/_update (source/engine/static/corrmap.py:578-736)
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef enum srx_bake_mode { SRX_BAKE_REPLACE = 0, SRX_BAKE_REPLACE_AVG = 1, SRX_BAKE_FIRST = 2, SRX_BAKE_FIRST_AVG = 3 } srx_bake_mode;
+typedef enum srx_bake_weight { SRX_WEIGHT_NONE = 0, /* reference behaviour: last pixel of the chosen frame wins */
+                               SRX_WEIGHT_UNIFORM = 1, SRX_WEIGHT_VIEW_NORMAL = 2, SRX_WEIGHT_VIEW_NORMAL_DEPTH = 3 } srx_bake_weight;
+
+typedef struct srx_bake_args {
+    void *values_dev;          /* fp16 [k2, Ht*Wt, C] atlas (corrmap.py:410), updated in place */
+    uint8_t *writtens_dev;     /* bool [k2, Ht*Wt] (corrmap.py:411) */
+    int k2, texels, channels;  /* k*k, Ht*Wt, C */
+    const void *colors_dev;    /* [F,H,W,Cin] */
+    int color_dtype;           /* SRX_F32 | SRX_F16 | SRX_BF16 */
+    int color_channels;        /* Cin (3 with C == 4 appends alpha = 1, corrmap.py:683-684; Cin > C truncates, :681-682) */
+    const void *ids_dev;       /* [F,H,W,4] */
+    int id_dtype;
+    const float *masks_dev;    /* [F,H,W] float32 or NULL; pixels with mask > 0 are kept (after inversion) */
+    int inverse_masks;         /* corrmap.py:651-654 */
+    int frames, height, width;
+    int sprite_id, material_id;/* -1 = no filter (None) */
+    int ignore_obj_mat_id;
+    int mode;                  /* srx_bake_mode */
+    int weight_mode;           /* srx_bake_weight; != NONE selects the weighted multi-view bake */
+    const void *normal_depth_dev; /* fp16 [F,H,W,4] for the VIEW_NORMAL* weights */
+    void *workspace_dev;       /* srx_bake_workspace_bytes() bytes */
+    int64_t workspace_bytes;
+} srx_bake_args;
+int64_t srx_bake_workspace_bytes(int k2, int texels, int channels, int weight_mode);
+/* Errors with SRX_ERR_INDEX (after a sync) when a kept pixel addresses a texel outside the atlas. */
+int srx_bake_update(const srx_bake_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Texture <-> tensor interop — replaces Texture._init_tensor/tensor/set_data (source/engine/static/texture/texture.py:166-254,
+ * 326-408: pycuda RegisteredImage + Memcpy2D + torch.cuda.synchronize) and the cuda-python wrappers of
+ * source/common_utils/cuda_utils.py:101-190.  The mapped cudaArray is read/written by kernels through a surface
+ * object on the caller's stream: no staging copy, no device-wide sync.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct srx_gl_resource srx_gl_resource;
+int srx_gl_register_image(srx_gl_resource **out, unsigned int gl_texture, unsigned int gl_target, unsigned int flags);
+int srx_gl_map(srx_gl_resource *res, void **cuda_array_out, void *stream);
+int srx_gl_unmap(srx_gl_resource *res, void *stream);
+int srx_gl_unregister(srx_gl_resource *res);
+/* array <-> linear tensor with the GL bottom-left -> top-left row flip (texture.py:236,253) fused in.
+ * `cuda_array` is a cudaArray_t (from srx_gl_map, or cudaMallocArray in tests); texel_bytes = channels * bytes per channel. */
+int srx_array_to_tensor(void *cuda_array, void *dst_dev, int width, int height, int texel_bytes, int flip, void *stream);
+int srx_tensor_to_array(void *cuda_array, const void *src_dev, int width, int height, int texel_bytes, int flip,
+                        int x_offset, int y_offset, void *stream);
+/* test helpers: plain cudaArray allocation so that the copy kernels can be exercised without a GL context */
+int srx_array_alloc(void **cuda_array_out, int width, int height, int channels, int bits_per_channel, int kind /*0 sint,1 uint,2 float*/);
+int srx_array_free(void *cuda_array);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRX_H_ */

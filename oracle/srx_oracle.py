@@ -493,9 +493,11 @@ def legacy_resize_overlap(frame_seq: np.ndarray, ids: np.ndarray, alpha: float, 
 
 def build_view_normal_map(normals: np.ndarray, view_vector: np.ndarray) -> np.ndarray:
     """``build_view_normal_map`` (overlap/utils.py:56-102) on float normals [T,H,W,3] in [0,1] (ToTensor scale):
-    |n · v/||v||| per pixel -> [T,H,W,1]."""
-    v = np.asarray(view_vector, dtype=np.float32).reshape(-1)
-    v = v / max(np.linalg.norm(v), 1e-12)
+    |n . normalize(view, dim=0)| per pixel -> [T,H,W,1].  ``F.normalize(v, p=2, dim=0)`` acts on the vector as given
+    (utils.py:97): a [1,3] vector is divided component-wise by max(|v_c|, 1e-12), a [3] vector by its length."""
+    v = np.asarray(view_vector, dtype=np.float32)
+    v = v / np.maximum(np.sqrt((v * v).sum(axis=0, keepdims=True)), 1e-12)
+    v = v.reshape(-1, 3)[0]
     return np.abs(np.einsum("thwc,c->thw", np.asarray(normals, dtype=np.float32), v))[..., None]
 
 

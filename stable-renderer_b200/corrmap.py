@@ -1,0 +1,342 @@
+"""`IDMap` and `CorrespondMap` with the reference's fields and method signatures
+(reference: source/engine/static/corrmap.py:49-280 and :373-736), backed by the CUDA kernels of libsrx.so.
+
+Differences that are deliberate:
+  * tensors live on a CUDA device; nothing here runs arithmetic on the CPU;
+  * OpenGL upload / binding methods (`load`, `bind`, `set_data`, corrmap.py:443-529) belong to the renderer, not to
+    this path, and are not provided;
+  * a 3-D id tensor handed to `CorrespondMap.update` is one frame (the reference loops forever, corrmap.py:629-630);
+  * mask + sprite/material filters are applied consistently (the reference re-indexes a compacted colour array with
+    original pixel indices, corrmap.py:715).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from functools import partial
+from pathlib import Path
+from typing import Literal, Optional, Sequence, TypeAlias
+
+import numpy as np
+import torch
+from attr import attrib, attrs
+from torch import Tensor
+
+from . import _lib
+
+UpdateMode: TypeAlias = Literal["replace", "replace_avg", "first", "first_avg"]
+BakeWeight: TypeAlias = Literal["none", "uniform", "view_normal", "view_normal_depth"]
+NO_ID_MAP_INDEX = 2048
+
+
+def extract_index(file_path, i):
+    """File-name ordering rule of the reference's dumps (source/common_utils/path_utils.py:173-179)."""
+    name = os.path.basename(file_path)
+    stem = name.split(".")[0]
+    if stem.split("_")[-1].isdigit():   # e.g. id_12.npy
+        return int(stem.split("_")[-1])
+    if name.split("_")[0].isdigit():    # e.g. 12_id.npy
+        return int(name.split("_")[0])
+    return i
+
+
+def _default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.SrxUnavailable("no CUDA device: the overlap / bake path has no CPU implementation")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+@attrs
+class IDMap:
+    """Per-frame correspondence ids (reference corrmap.py:49-136).
+
+    tensor [N,H,W,4] = (spriteID, materialID, map_index, vertexID); `masks` [N,H,W] float32, 1 = no id."""
+
+    tensor: Tensor = attrib()
+    frame_indices: list = attrib(default=None)
+    masks: Tensor = attrib(default=None)
+    _vertex_screen_info_cache: Tensor = attrib(default=None, init=False)
+    _plans: dict = attrib(factory=dict, init=False, repr=False)
+    _device_ids: dict = attrib(factory=dict, init=False, repr=False)
+
+    @property
+    def frame_count(self) -> int:
+        return len(self.frame_indices)
+
+    def __getitem__(self, index: int) -> Tensor:
+        return self.tensor[index]
+
+    def __len__(self):
+        return self.frame_count
+
+    @property
+    def height(self) -> int:  # same (surprising) definition as corrmap.py:85-88 for NHWC ids
+        return self.tensor.shape[-2]
+
+    @property
+    def width(self) -> int:   # corrmap.py:90-93
+        return self.tensor.shape[-1]
+
+    def __attrs_post_init__(self):
+        if self.frame_indices is None and self.tensor is not None:
+            if not isinstance(self.tensor, torch.Tensor):
+                raise ValueError("Invalid type of real ID tensor.")
+            if self.tensor.dim() == 4:
+                n = self.tensor.shape[0]
+            elif self.tensor.dim() == 3:
+                n = 1
+            else:
+                raise ValueError("Invalid shape of real ID tensor.")
+            self.frame_indices = list(range(n))
+        elif isinstance(self.frame_indices, int):
+            self.frame_indices = [self.frame_indices]
+        if isinstance(self.tensor, torch.Tensor) and self.tensor.dim() == 3:
+            self.tensor = torch.stack([self.tensor] * len(self.frame_indices), dim=0)
+        if self.masks is None:
+            if self.tensor is not None:   # corrmap.py:119-124
+                no_id = (self.tensor[..., 2] == NO_ID_MAP_INDEX) | torch.all(self.tensor == 0, dim=-1)
+                self.masks = no_id.to(torch.float32)
+        elif self.masks.dim() == 2:
+            self.masks = torch.stack([self.masks] * self.frame_count, dim=0)
+
+    def __deepcopy__(self, memo=None):
+        return IDMap(frame_indices=list(self.frame_indices), tensor=self.tensor.clone(),
+                     masks=self.masks.clone() if self.masks is not None else None)
+
+    @classmethod
+    def from_directory(cls, directory, frame_start: int | None = None, num_frames: int | None = None,
+                       use_frame_indices_from_filename: bool = True, device=None) -> "IDMap":
+        """Loads `id_N.npy` dumps ordered by `extract_index` (reference corrmap.py:138-198)."""
+        assert os.path.exists(directory)
+        frame_start = frame_start or 0
+        filenames = [f for f in os.listdir(directory) if f.endswith(".npy")]
+        ordered = sorted(filenames, key=lambda x: extract_index(x, filenames.index(x)))
+        if use_frame_indices_from_filename:
+            frame_indices = list(map(partial(extract_index, i=-1), ordered))
+        else:
+            frame_indices = list(range(len(ordered)))
+        num_frames = num_frames or len(frame_indices)
+        frame_indices = frame_indices[frame_start: frame_start + num_frames]
+        assert all(i != -1 for i in frame_indices), "Illegal filename(s) found."
+        tensors = []
+        for name in ordered[frame_start: frame_start + num_frames]:
+            t = torch.from_numpy(np.load(os.path.join(directory, name))).squeeze()
+            if t.dim() != 3:
+                raise ValueError(f"Invalid shape of id tensor: {t.shape}.")
+            if not (t.shape[-1] == 4 or t.shape[1] == 4):
+                raise ValueError(f"Invalid id tensor shape: {t.shape}.")
+            tensors.append(t)
+        if len(tensors) == 0:
+            raise ValueError("No valid id data found.")
+        if any(t.shape != tensors[0].shape for t in tensors):
+            raise ValueError("Tensor data has inconsistent shapes.")
+        t = torch.stack(tensors, dim=0)
+        if device is not None:
+            t = t.to(device)
+        return cls(frame_indices=frame_indices, tensor=t)
+
+    @classmethod
+    def from_tensor(cls, frame_indices: list, tensor: Tensor) -> "IDMap":
+        if tensor.dim() != 4:
+            raise ValueError(f"Tensor should be in (B, H, W, C), got shape {tensor.shape}")
+        if len(frame_indices) != tensor.shape[0]:
+            raise ValueError(f"Frame indices count should be equal to the batch size of the tensor, got "
+                             f"{len(frame_indices)} and {tensor.shape[0]}")
+        return cls(frame_indices=frame_indices, tensor=tensor)
+
+    # -- device plumbing -------------------------------------------------------------------------------------
+    def device_ids(self, device: torch.device) -> Tensor:
+        """The id buffers on `device` as contiguous int32/int16 (cached; the reference moves the derived
+        vertex_screen_info instead, corresponder.py:309)."""
+        device = torch.device(device)
+        t = self._device_ids.get(device)
+        if t is None:
+            t = self.tensor
+            if t.dtype not in (torch.int32, torch.int16):
+                t = t.to(torch.int32)
+            t = t.to(device).contiguous()
+            self._device_ids[device] = t
+        return t
+
+    def create_vertex_screen_info(self) -> Tensor:
+        """[N,7] float32 (object, material, map_index, vertex_id, x/H, y/W, frame_index) in (frame,y,x) order —
+        bit-identical to the reference's tensor (corrmap.py:220-280), built by `srx_vertex_screen_info`."""
+        if self._vertex_screen_info_cache is None:
+            dev = self.tensor.device if self.tensor.is_cuda else _default_device()
+            ids = self.device_ids(dev)
+            F, H, W, _ = ids.shape
+            out = torch.empty(F * H * W, 7, dtype=torch.float32, device=dev)
+            n = C.c_int64(0)
+            fv = (C.c_int32 * F)(*[int(v) for v in self.frame_indices])
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().srx_vertex_screen_info(ids.data_ptr(), _lib.torch_dtype_code(ids.dtype), F, H, W, fv,
+                                                              out.data_ptr(), C.byref(n), _lib.current_stream_ptr(dev)))
+            self._vertex_screen_info_cache = out[: n.value].clone().to(self.tensor.device)
+        return self._vertex_screen_info_cache
+
+
+@attrs(repr=False, eq=False)
+class CorrespondMap:
+    """The UV-texture atlas (reference corrmap.py:373-411): `_values` fp16 [k*k, height*width, C] and
+    `_writtens` bool [k*k, height*width], vertexID = width*y + x."""
+
+    name: Optional[str] = attrib(default=None)
+    k: int = attrib(default=3, kw_only=True)
+    height: int = attrib(default=512, kw_only=True)
+    width: int = attrib(default=512, kw_only=True)
+    channel_count: int = attrib(default=4, kw_only=True)
+    device: Optional[torch.device] = attrib(default=None, kw_only=True)
+    _values: Tensor = attrib(init=False)
+    _writtens: Tensor = attrib(init=False)
+    vertex_screen_info: Optional[Tensor] = attrib(default=None, init=False)
+    _workspace: Optional[Tensor] = attrib(default=None, init=False)
+
+    def __attrs_post_init__(self):
+        self.device = torch.device(self.device) if self.device is not None else _default_device()
+        self._values = torch.zeros(self.k * self.k, self.height * self.width, self.channel_count, dtype=torch.float16,
+                                   device=self.device)
+        self._writtens = torch.zeros(self.k * self.k, self.height * self.width, dtype=torch.bool, device=self.device)
+
+    def __repr__(self):
+        return f"<CorrespondMap: {self.name or 'untitled'}, k={self.k}, size={self.height}x{self.width}, channel_count={self.channel_count}>"
+
+    def __getitem__(self, index):
+        return self._values[index]
+
+    def clear(self):
+        self._values.zero_()
+        self._writtens.zero_()
+
+    def numpy_data(self, map_index: int, width: int | None = None, height: int | None = None, dtype=np.float16):
+        return self.get_map(map_index, height, width).cpu().numpy().astype(dtype)
+
+    def get_map(self, index: int, height: int | None = None, width: int | None = None,
+                order: Literal["whc", "hwc"] = "hwc"):
+        height = height or self.height
+        width = width or self.width
+        assert height * width <= self.height * self.width, "The given size is larger than the original size."
+        if height * width < self.height * self.width:
+            return self._values[index, : width * height].view(height, width, self.channel_count)
+        data = self._values[index].view(height, width, self.channel_count)
+        if order == "whc":
+            data = data.permute(1, 0, 2)
+        return data
+
+    def get_maps(self, height: int | None = None, width: int | None = None):
+        width = self.width if width is None else width
+        height = self.height if height is None else height
+        if width * height < self.width * self.height:
+            return self._values[:, : width * height].view(self.k * self.k, height, width, self.channel_count)
+        return self._values.view(self.k * self.k, height, width, self.channel_count)
+
+    def get_written_flag_map(self, index: int, height: int | None = None, width: int | None = None):
+        height = self.height if height is None else height
+        width = self.width if width is None else width
+        if height * width < self.height * self.width:
+            return self._writtens[index, : width * height].view(height, width)
+        return self._writtens[index].view(height, width)
+
+    # -- the bake ------------------------------------------------------------------------------------------------
+    def update(self, color_frames, id_maps, spriteID: int | None = None, materialID: int | None = None,
+               mode: UpdateMode = "first_avg", masks=None, inverse_masks: bool = False, ignore_obj_mat_id: bool = False,
+               weight_mode: BakeWeight = "none", normal_depth: Optional[Tensor] = None):
+        """`CorrespondMap.update` (reference corrmap.py:578-670): same arguments; all frames go to the GPU in one call.
+
+        weight_mode / normal_depth select the depth/normal-weighted multi-view bake, which the
+        reference lists as TODO (README.md:18-19); "none" is the reference behaviour."""
+        if mode not in ("replace", "replace_avg", "first", "first_avg"):
+            raise ValueError(f"unknown update mode {mode}")
+        colors = self._stack(color_frames, "color_frames")
+        if isinstance(id_maps, IDMap):
+            id_maps = id_maps.tensor
+        if isinstance(id_maps, (list, tuple)):
+            id_maps = [m.tensor if isinstance(m, IDMap) else m for m in id_maps]
+        ids = self._stack(id_maps, "id_maps")
+        if colors.shape[0] != ids.shape[0]:
+            raise ValueError(f"The length of color_frames and id_maps should be the same, but got: {colors.shape[0]} and {ids.shape[0]}")
+        if colors.shape[1:3] != ids.shape[1:3]:
+            raise ValueError(f"colour frames {tuple(colors.shape)} and id maps {tuple(ids.shape)} differ in size")
+        mk = None
+        if masks is not None:
+            if isinstance(masks, (list, tuple)):
+                masks = torch.stack([m.squeeze() for m in masks], dim=0)
+            if not isinstance(masks, Tensor):
+                raise ValueError("Invalid type of masks. Got: ", type(masks))
+            if masks.dim() == 4 and masks.shape[-1] == 1:
+                masks = masks.squeeze(-1)
+            elif masks.dim() == 3 and masks.shape[-1] == 1 and ids.shape[0] == 1:
+                masks = masks.squeeze(-1).unsqueeze(0)
+            if masks.dim() == 2:
+                masks = masks.unsqueeze(0)
+            if masks.dim() != 3:
+                raise ValueError("The shape of masks is invalid. Got: ", masks.shape)
+            if masks.shape[0] != colors.shape[0]:
+                raise ValueError(f"The length of masks should be the same as color_frames, but got: {masks.shape[0]} and {colors.shape[0]}")
+            mk = masks.to(device=self.device, dtype=torch.float32).contiguous()
+        if ids.dtype not in (torch.int32, torch.int16):
+            ids = ids.to(torch.int32)
+        ids = ids.to(self.device).contiguous()
+        if colors.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            colors = colors.to(torch.float32)
+        colors = colors.to(self.device).contiguous()
+        nd = None
+        if weight_mode in ("view_normal", "view_normal_depth"):
+            if normal_depth is None:
+                raise ValueError(f"weight_mode={weight_mode} needs the normal+depth attachment")
+            nd = normal_depth.to(device=self.device, dtype=torch.float16).contiguous()
+            if nd.shape[:3] != ids.shape[:3] or nd.shape[-1] != 4:
+                raise ValueError("normal_depth must be [F,H,W,4]")
+        lib = _lib.load()
+        wm = _lib.SRX_BAKE_WEIGHT[weight_mode]
+        need = int(lib.srx_bake_workspace_bytes(self.k * self.k, self.height * self.width, self.channel_count, wm))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        a = _lib.srx_bake_args()
+        a.values_dev = self._values.data_ptr()
+        a.writtens_dev = self._writtens.data_ptr()
+        a.k2, a.texels, a.channels = self.k * self.k, self.height * self.width, self.channel_count
+        a.colors_dev, a.color_dtype, a.color_channels = colors.data_ptr(), _lib.torch_dtype_code(colors.dtype), colors.shape[-1]
+        a.ids_dev, a.id_dtype = ids.data_ptr(), _lib.torch_dtype_code(ids.dtype)
+        a.masks_dev = mk.data_ptr() if mk is not None else None
+        a.inverse_masks = 1 if inverse_masks else 0
+        a.frames, a.height, a.width = ids.shape[0], ids.shape[1], ids.shape[2]
+        a.sprite_id = -1 if spriteID is None else int(spriteID)
+        a.material_id = -1 if materialID is None else int(materialID)
+        a.ignore_obj_mat_id = 1 if ignore_obj_mat_id else 0
+        a.mode = _lib.SRX_BAKE_MODE[mode]
+        a.weight_mode = wm
+        a.normal_depth_dev = nd.data_ptr() if nd is not None else None
+        a.workspace_dev, a.workspace_bytes = self._workspace.data_ptr(), self._workspace.numel()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.srx_bake_update(C.byref(a), _lib.current_stream_ptr(self.device)))
+
+    @staticmethod
+    def _stack(frames, what: str) -> Tensor:
+        if isinstance(frames, Tensor):
+            if frames.dim() == 4:
+                return frames
+            if frames.dim() == 3:
+                return frames.unsqueeze(0)
+            raise ValueError(f"The shape of {what} is invalid. Got: ", frames.shape)
+        if isinstance(frames, (list, tuple)):
+            parts = []
+            for f in frames:
+                if f.dim() == 4:
+                    parts.append(f)
+                elif f.dim() == 3:
+                    parts.append(f.unsqueeze(0))
+                else:
+                    raise ValueError(f"The shape of {what} is invalid. Got: ", f.shape)
+            return torch.cat(parts, dim=0)
+        raise ValueError(f"Invalid type of {what}. Got: ", type(frames))
+
+    def load_vertex_screen_info(self, id_map: IDMap):
+        self.vertex_screen_info = id_map.create_vertex_screen_info()
+
+    @property
+    def unique_vertex_ids(self) -> Tensor:
+        assert self.vertex_screen_info is not None, "Vertex screen positions are not loaded."
+        return self.vertex_screen_info[..., 3].unique()
+
+
+__all__ = ["IDMap", "UpdateMode", "CorrespondMap", "extract_index"]

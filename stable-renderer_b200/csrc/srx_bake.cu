@@ -1,0 +1,230 @@
+// srx_bake.cu — UV-texture bake: projects decoded frames into the CorrespondMap atlas.
+//
+// Replaces CorrespondMap.update / _update (source/engine/static/corrmap.py:578-736), called from
+// DefaultCorresponder.finished (source/common_utils/stable_render_utils/corresponder.py:130-155).
+//
+// Reference semantics (frames strictly sequential; within a frame `index_put_` with duplicate texels):
+//   replace*: a texel ends with the colour of the LAST kept pixel (row-major) of the LAST frame that touches it;
+//   first*  : texels written before the call are skipped (corrmap.py:720-725); otherwise the last kept pixel of the
+//             EARLIEST frame that touches the texel.
+// Both are "max over an order key", so all frames are processed in parallel:
+//   B1 claim : owner[texel] = atomicMax(order(frame, pixel) + 1)          ids (+mask) streamed once
+//   B2 write : the pixel whose order equals owner[texel] converts its colour to fp16 and stores it
+// The weighted multi-view bake (not in the reference) replaces B1/B2 with a vector-atomic
+// weighted sum per texel and a per-texel finalize.
+#include "srx_common.cuh"
+
+enum { BK_ST_INDEX = 0 };
+
+struct BakeGeom {
+    int k2, texels, C, Cin;
+    int H, W;
+    int sprite, material, ignore_filter;
+    int inverse_masks;
+    int first_mode;
+    int frames_total;  // frames in this chunk
+};
+
+template <typename IdT>
+__device__ __forceinline__ bool bake_texel(const IdT *__restrict__ ids, const float *__restrict__ masks, long long i,
+                                           const BakeGeom &g, bool require_id, long long *tex, int *status) {
+    if (masks) {
+        float m = masks[i];
+        if (g.inverse_masks) m = __fsub_rn(1.f, m);  // corrmap.py:651-654
+        if (!(m > 0.f)) return false;                // corrmap.py:707
+    }
+    const IdPx p = load_id(ids + i);
+    if (require_id && !id_valid(p)) return false;
+    if (!g.ignore_filter) {                         // corrmap.py:710-715
+        if (g.sprite >= 0 && p.s != g.sprite) return false;
+        if (g.material >= 0 && p.m != g.material) return false;
+    }
+    int mi = p.i, vid = p.v;
+    if (mi < 0) mi += g.k2;          // torch negative-index wrap
+    if (vid < 0) vid += g.texels;
+    if (mi < 0 || mi >= g.k2 || vid < 0 || vid >= g.texels) {
+        atomicOr(status + BK_ST_INDEX, 1);  // the reference raises IndexError at corrmap.py:723/735
+        return false;
+    }
+    *tex = (long long)mi * g.texels + vid;
+    return true;
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(256) k_bake_claim(const IdT *__restrict__ ids, const float *__restrict__ masks,
+                                                     const uint8_t *__restrict__ writtens, unsigned int *__restrict__ owner,
+                                                     int *__restrict__ status, BakeGeom g, long long npx) {
+    const long long hw = (long long)g.H * g.W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        long long tex;
+        if (!bake_texel(ids, masks, i, g, false, &tex, status)) continue;
+        if (g.first_mode && writtens[tex]) continue;
+        const long long f = i / hw, pix = i - f * hw;
+        const long long order = (g.first_mode ? (g.frames_total - 1 - f) : f) * hw + pix;
+        atomicMax(owner + tex, (unsigned int)(order + 1));
+    }
+}
+
+template <typename CT> __device__ __forceinline__ float color_ld(const CT *p);
+template <> __device__ __forceinline__ float color_ld<float>(const float *p) { return __ldg(p); }
+template <> __device__ __forceinline__ float color_ld<__half>(const __half *p) { return __half2float(*p); }
+template <> __device__ __forceinline__ float color_ld<__nv_bfloat16>(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+
+template <typename IdT, typename CT>
+__global__ void __launch_bounds__(256) k_bake_write(const IdT *__restrict__ ids, const float *__restrict__ masks,
+                                                     const CT *__restrict__ colors, uint8_t *__restrict__ writtens,
+                                                     const unsigned int *__restrict__ owner, __half *__restrict__ values,
+                                                     int *__restrict__ status, BakeGeom g, long long npx) {
+    const long long hw = (long long)g.H * g.W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        long long tex;
+        if (!bake_texel(ids, masks, i, g, false, &tex, status)) continue;
+        const long long f = i / hw, pix = i - f * hw;
+        const long long order = (g.first_mode ? (g.frames_total - 1 - f) : f) * hw + pix;
+        if (owner[tex] != (unsigned int)(order + 1)) continue;  // in first mode owner stays 0 for already-written texels
+        const CT *c = colors + i * g.Cin;
+        __half *v = values + tex * g.C;
+        for (int ch = 0; ch < g.C; ++ch)  // channel fix-up of corrmap.py:681-684
+            v[ch] = __float2half_rn(ch < g.Cin ? color_ld<CT>(c + ch) : 1.f);
+        writtens[tex] = 1;
+    }
+}
+
+// ---- weighted multi-view bake -----------------------------------------------------------------------------------
+__device__ __forceinline__ float bake_weight(const __half *__restrict__ nd, long long i, int mode) {
+    if (mode == SRX_WEIGHT_UNIFORM || nd == nullptr) return 1.f;
+    const float nz = __half2float(nd[i * 4 + 2]);
+    const float vn = fabsf(__fsub_rn(__fmul_rn(2.f, nz), 1.f));         // |n . (0,0,1)| of the *0.5+0.5 encoded normal
+    float w = __fdiv_rn(1.f, __fadd_rn(fabsf(__fsub_rn(1.f, vn)), 1.f));  // algorithms.py:111-113
+    if (mode == SRX_WEIGHT_VIEW_NORMAL_DEPTH) w = __fmul_rn(w, __half2float(nd[i * 4 + 3]));
+    return w;
+}
+
+template <typename IdT, typename CT>
+__global__ void __launch_bounds__(256) k_bake_accum(const IdT *__restrict__ ids, const float *__restrict__ masks,
+                                                     const CT *__restrict__ colors, const __half *__restrict__ nd,
+                                                     float *__restrict__ acc, float *__restrict__ wsum,
+                                                     int *__restrict__ status, BakeGeom g, int weight_mode, long long npx) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        long long tex;
+        if (!bake_texel(ids, masks, i, g, true, &tex, status)) continue;
+        const float w = bake_weight(nd, i, weight_mode);
+        const CT *c = colors + i * g.Cin;
+        float v[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) v[ch] = ch < g.C ? __fmul_rn(w, ch < g.Cin ? color_ld<CT>(c + ch) : 1.f) : 0.f;
+        red_add_f32x4(acc + tex * 4, v[0], v[1], v[2], v[3]);
+        red_add_f32(wsum + tex, w);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bake_finalize(const float *__restrict__ acc, const float *__restrict__ wsum,
+                                                        __half *__restrict__ values, uint8_t *__restrict__ writtens,
+                                                        long long ntex, int C, int first_mode) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntex; t += (long long)gridDim.x * blockDim.x) {
+        const float w = wsum[t];
+        if (!(w > 0.f)) continue;
+        if (first_mode && writtens[t]) continue;
+        for (int ch = 0; ch < C; ++ch) values[t * C + ch] = __float2half_rn(__fdiv_rn(acc[t * 4 + ch], w));
+        writtens[t] = 1;
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------
+static inline int64_t bk_align(int64_t v) { return (v + 255) / 256 * 256; }
+
+extern "C" int64_t srx_bake_workspace_bytes(int k2, int texels, int channels, int weight_mode) {
+    (void)channels;
+    const int64_t ntex = (int64_t)k2 * texels;
+    if (weight_mode == SRX_WEIGHT_NONE) return bk_align(ntex * 4) + 256;
+    return bk_align(ntex * 16) + bk_align(ntex * 4) + 256;
+}
+
+template <typename IdT, typename CT>
+static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
+    const int64_t ntex = (int64_t)a->k2 * a->texels;
+    const long long hw = (long long)a->height * a->width;
+    char *ws = reinterpret_cast<char *>(a->workspace_dev);
+    BakeGeom g;
+    g.k2 = a->k2; g.texels = a->texels; g.C = a->channels; g.Cin = a->color_channels;
+    g.H = a->height; g.W = a->width;
+    g.sprite = a->sprite_id; g.material = a->material_id; g.ignore_filter = a->ignore_obj_mat_id;
+    g.inverse_masks = a->inverse_masks;
+    g.first_mode = (a->mode == SRX_BAKE_FIRST || a->mode == SRX_BAKE_FIRST_AVG) ? 1 : 0;
+    const int sms = srx_sm_count_cached();
+    const IdT *ids = reinterpret_cast<const IdT *>(a->ids_dev);
+    const CT *colors = reinterpret_cast<const CT *>(a->colors_dev);
+    __half *values = reinterpret_cast<__half *>(a->values_dev);
+    int *status;
+    if (a->weight_mode == SRX_WEIGHT_NONE) {
+        unsigned int *owner = reinterpret_cast<unsigned int *>(ws);
+        status = reinterpret_cast<int *>(ws + bk_align(ntex * 4));
+        SRX_CUDA_CHECK(cudaMemsetAsync(status, 0, 256, st));
+        // the 32-bit order key holds frames_per_chunk*H*W + 1; longer sequences run as ordered chunks
+        const long long max_frames = ((1ll << 32) - 2) / hw;
+        SRX_REQUIRE(max_frames >= 1, SRX_ERR_UNSUPPORTED, "frame larger than 2^32 pixels");
+        const int step = (int)(max_frames < a->frames ? max_frames : a->frames);
+        for (int f0 = 0; f0 < a->frames; f0 += step) {
+            const int nf = a->frames - f0 < step ? a->frames - f0 : step;
+            g.frames_total = nf;
+            const long long npx = (long long)nf * hw;
+            long long nb = (npx + 255) / 256;
+            const int grid = (int)(nb < (long long)sms * 8 ? nb : (long long)sms * 8);
+            const float *masks = a->masks_dev ? a->masks_dev + (long long)f0 * hw : nullptr;
+            SRX_CUDA_CHECK(cudaMemsetAsync(owner, 0, (size_t)ntex * 4, st));
+            k_bake_claim<IdT><<<grid, 256, 0, st>>>(ids + (long long)f0 * hw, masks, a->writtens_dev, owner, status, g, npx);
+            k_bake_write<IdT, CT><<<grid, 256, 0, st>>>(ids + (long long)f0 * hw, masks, colors + (long long)f0 * hw * g.Cin,
+                                                        a->writtens_dev, owner, values, status, g, npx);
+        }
+    } else {
+        float *acc = reinterpret_cast<float *>(ws);
+        float *wsum = reinterpret_cast<float *>(ws + bk_align(ntex * 16));
+        status = reinterpret_cast<int *>(ws + bk_align(ntex * 16) + bk_align(ntex * 4));
+        SRX_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)(bk_align(ntex * 16) + bk_align(ntex * 4) + 256), st));
+        g.frames_total = a->frames;
+        const long long npx = (long long)a->frames * hw;
+        long long nb = (npx + 255) / 256;
+        const int grid = (int)(nb < (long long)sms * 8 ? nb : (long long)sms * 8);
+        k_bake_accum<IdT, CT><<<grid, 256, 0, st>>>(ids, a->masks_dev, colors, reinterpret_cast<const __half *>(a->normal_depth_dev),
+                                                    acc, wsum, status, g, a->weight_mode, npx);
+        long long nb2 = (ntex + 255) / 256;
+        const int grid2 = (int)(nb2 < (long long)sms * 8 ? nb2 : (long long)sms * 8);
+        k_bake_finalize<<<grid2, 256, 0, st>>>(acc, wsum, values, a->writtens_dev, ntex, g.C, g.first_mode);
+    }
+    SRX_CUDA_CHECK(cudaGetLastError());
+    int st_host = 0;
+    SRX_CUDA_CHECK(cudaMemcpyAsync(&st_host, status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SRX_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (st_host)
+        return srx_set_error(SRX_ERR_INDEX, "index out of range: a kept pixel addresses (map_index, vertexID) outside the "
+                             "%d x %d atlas (corrmap.py:735)", a->k2, a->texels);
+    return SRX_OK;
+}
+
+template <typename IdT>
+static int bake_color_dispatch(const srx_bake_args *a, cudaStream_t st) {
+    switch (a->color_dtype) {
+        case SRX_F32: return bake_impl<IdT, float>(a, st);
+        case SRX_F16: return bake_impl<IdT, __half>(a, st);
+        case SRX_BF16: return bake_impl<IdT, __nv_bfloat16>(a, st);
+        default: return srx_set_error(SRX_ERR_INVALID, "colour dtype must be f32/f16/bf16");
+    }
+}
+
+extern "C" int srx_bake_update(const srx_bake_args *a, void *stream) {
+    SRX_REQUIRE(a, SRX_ERR_INVALID, "null argument");
+    SRX_REQUIRE(a->values_dev && a->writtens_dev && a->colors_dev && a->ids_dev && a->workspace_dev, SRX_ERR_INVALID, "null buffer");
+    SRX_REQUIRE(a->k2 > 0 && a->texels > 0 && a->channels > 0 && a->channels <= 4, SRX_ERR_INVALID, "atlas must have 1..4 channels");
+    SRX_REQUIRE(a->frames > 0 && a->height > 0 && a->width > 0 && a->color_channels > 0, SRX_ERR_INVALID, "non-positive dimension");
+    SRX_REQUIRE(a->mode >= SRX_BAKE_REPLACE && a->mode <= SRX_BAKE_FIRST_AVG, SRX_ERR_INVALID, "unknown update mode");
+    SRX_REQUIRE(a->weight_mode >= SRX_WEIGHT_NONE && a->weight_mode <= SRX_WEIGHT_VIEW_NORMAL_DEPTH, SRX_ERR_INVALID, "unknown weight mode");
+    // channel fix-up (corrmap.py:681-684): truncate, or append alpha = 1 when C == 4 and the colour has 3 channels
+    SRX_REQUIRE(a->color_channels >= a->channels || (a->channels == 4 && a->color_channels == 3), SRX_ERR_INVALID,
+                "shape mismatch: colour has %d channels, atlas has %d", a->color_channels, a->channels);
+    SRX_REQUIRE(a->weight_mode < SRX_WEIGHT_VIEW_NORMAL || a->normal_depth_dev, SRX_ERR_INVALID, "normal/depth buffer required for this weight mode");
+    SRX_REQUIRE(a->workspace_bytes >= srx_bake_workspace_bytes(a->k2, a->texels, a->channels, a->weight_mode), SRX_ERR_INVALID, "workspace too small");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a->id_dtype == SRX_I32) return bake_color_dispatch<int4>(a, st);
+    if (a->id_dtype == SRX_I16) return bake_color_dispatch<short4>(a, st);
+    return srx_set_error(SRX_ERR_INVALID, "id dtype must be int32 or int16");
+}

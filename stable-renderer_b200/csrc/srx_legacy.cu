@@ -1,0 +1,321 @@
+// srx_legacy.cu — legacy-generation overlap: full-tuple keys, four weighting strategies.
+//
+// Replaces (reference paths relative to /root/reference/legacy_codes/stable_rendering_algo):
+//   CorrespondenceMap.FromExisting / merge_nearby   data_classes/correspondence_map.py:145-170, 276-286
+//   Overlap.__call__ (kernel_radius 0)              overlap/overlap.py:83-152
+//   ResizeOverlap.__call__                          overlap/overlap.py:180-222
+//   AverageDistance / FrameDistance / PixelDistance / PerpendicularViewNormal   overlap/algorithms.py:34-118
+//
+// The reference up-samples the latents to the id resolution, walks a Python dict of per-key traces doing an [L,L]
+// weight matmul for each, and down-samples again.  Only ONE id pixel per latent cell survives the nearest
+// down-sample, so the work is restated gather-side:
+//   L0 seed     : every latent cell looks at the id pixel it will be sampled from, packs its id tuple into an exact
+//                 64-bit key and inserts it into an L2-resident open-addressing table (atomicCAS); cells sharing a
+//                 key are chained.  Keys that no sampled pixel carries are never stored.
+//   L1 accum    : one streaming pass over all id pixels (coalesced 128-bit loads).  A pixel whose key is in the
+//                 table adds weight(i,j) * latent_j into the record of every chained cell i (vector atomics) —
+//                 the row of the reference's weight matrix that belongs to cell i, without materialising it.
+//   L2 finalize : ov = sum / weight-sum (or sum / (L * w_i) for the view-normal strategy, algorithms.py:114-117),
+//                 alpha blend, `where(out != 0, out, original)` (overlap.py:221), in-place write.
+#include "srx_common.cuh"
+#include <vector>
+
+#define LG_EMPTY 0xFFFFFFFFFFFFFFFFull
+enum { LG_ST_KEY = 0 };
+
+struct LegacyGeom {
+    int T, H, W, h, w, C;
+    int merge;      // >= 1
+    int strategy;
+    int resize;     // 1: ResizeOverlap (apply where()), 0: Overlap at id resolution
+    unsigned int mask;  // table capacity - 1
+};
+
+__device__ __forceinline__ int floordiv(int a, int b) {
+    int q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+    return q;
+}
+
+// exact 64-bit packing of the id tuple (after merge_nearby's floor division of components 2 and 3)
+template <typename IdT> __device__ __forceinline__ bool pack_key(const IdPx &p, int merge, unsigned long long *key);
+template <> __device__ __forceinline__ bool pack_key<short4>(const IdPx &p, int merge, unsigned long long *key) {
+    const int a = floordiv(p.i, merge), b = floordiv(p.v, merge);
+    *key = ((unsigned long long)(unsigned short)p.s << 48) | ((unsigned long long)(unsigned short)p.m << 32) |
+           ((unsigned long long)(unsigned short)a << 16) | (unsigned long long)(unsigned short)b;
+    return true;  // 4 x 16 bits: always exact
+}
+template <> __device__ __forceinline__ bool pack_key<int4>(const IdPx &p, int merge, unsigned long long *key) {
+    const int a = floordiv(p.i, merge), b = floordiv(p.v, merge);
+    if (p.s < 0 || p.s >= 1024 || p.m < 0 || p.m >= 1024 || a < 0 || a >= 4096 || b < 0) return false;
+    *key = ((unsigned long long)p.s << 54) | ((unsigned long long)p.m << 44) | ((unsigned long long)a << 32) |
+           (unsigned long long)(unsigned int)b;
+    return true;
+}
+
+__device__ __forceinline__ unsigned int hash64(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (unsigned int)k;
+}
+
+__device__ __forceinline__ float vn_weight(float vn) {  // algorithms.py:111-113
+    return __fdiv_rn(1.f, __fadd_rn(fabsf(__fsub_rn(1.f, vn)), 1.f));
+}
+
+struct LegacyBufs {
+    unsigned long long *keys;  // [cap]
+    int *head;                 // [cap] first chained cell, -1 = none
+    int *next;                 // [ncell]
+    int *cellslot;             // [ncell] table slot of the cell's key, -1 = the sampled pixel has no id
+    float *selfx;              // [ncell][C] latent seen through the resize round trip
+    float *sum;                // [ncell][C]
+    float *wsum;               // [ncell]
+    float *cnt;                // [ncell]  L
+    float *wself;              // [ncell]  w_i (view-normal)
+    int *up_y, *up_x, *down_y, *down_x;
+    int *status;
+};
+
+template <typename IdT, typename XT>
+__global__ void __launch_bounds__(256) k_legacy_seed(const IdT *__restrict__ ids, const XT *__restrict__ x,
+                                                      const float *__restrict__ vnmap, LegacyBufs b, LegacyGeom g, long long ncell) {
+    for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < ncell; cell += (long long)gridDim.x * blockDim.x) {
+        const int sx = (int)(cell % g.w);
+        const long long t = cell / g.w;
+        const int sy = (int)(t % g.h);
+        const int f = (int)(t / g.h);
+        const int py = b.down_y[sy], px = b.down_x[sx];
+        const long long pix = ((long long)f * g.H + py) * g.W + px;
+        const int uy = b.up_y[py], ux = b.up_x[px];
+        for (int c = 0; c < g.C; ++c)
+            b.selfx[cell * g.C + c] = XIo<XT>::ld(x + (((long long)f * g.C + c) * g.h + uy) * g.w + ux);
+        const IdPx p = load_id(ids + pix);
+        int slot = -1;
+        if ((p.s | p.m | p.i | p.v) != 0) {  // correspondence_map.py:153 — only all-zero ids are skipped
+            unsigned long long key;
+            if (!pack_key<IdT>(p, g.merge, &key)) {
+                atomicOr(b.status + LG_ST_KEY, 1);
+            } else {
+                unsigned int s = hash64(key) & g.mask;
+                while (true) {
+                    const unsigned long long prev = atomicCAS(b.keys + s, LG_EMPTY, key);
+                    if (prev == LG_EMPTY || prev == key) break;
+                    s = (s + 1) & g.mask;
+                }
+                slot = (int)s;
+                b.next[cell] = atomicExch(b.head + s, (int)cell);
+                if (g.strategy == SRX_STRATEGY_VIEW_NORMAL) b.wself[cell] = vn_weight(vnmap[pix]);
+            }
+        }
+        b.cellslot[cell] = slot;
+    }
+}
+
+template <typename IdT, typename XT>
+__global__ void __launch_bounds__(256) k_legacy_accum(const IdT *__restrict__ ids, const XT *__restrict__ x,
+                                                       const float *__restrict__ vnmap, LegacyBufs b, LegacyGeom g, long long npx) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < npx; j += (long long)gridDim.x * blockDim.x) {
+        const IdPx p = load_id(ids + j);
+        if ((p.s | p.m | p.i | p.v) == 0) continue;
+        unsigned long long key;
+        if (!pack_key<IdT>(p, g.merge, &key)) { atomicOr(b.status + LG_ST_KEY, 1); continue; }
+        unsigned int s = hash64(key) & g.mask;
+        bool found = false;
+        while (true) {
+            const unsigned long long k = b.keys[s];
+            if (k == key) { found = true; break; }
+            if (k == LG_EMPTY) break;
+            s = (s + 1) & g.mask;
+        }
+        if (!found) continue;  // no latent cell samples this surface point: nothing downstream reads its sum
+        const int xj = (int)(j % g.W);
+        const long long t = j / g.W;
+        const int yj = (int)(t % g.H);
+        const int fj = (int)(t / g.H);
+        const XT *xp = x + (((long long)fj * g.C) * g.h + b.up_y[yj]) * g.w + b.up_x[xj];
+        const long long plane = (long long)g.h * g.w;
+        float wj = 1.f;
+        if (g.strategy == SRX_STRATEGY_VIEW_NORMAL) wj = vn_weight(vnmap[j]);
+        for (int i = b.head[s]; i >= 0; i = b.next[i]) {
+            float wgt = wj;
+            if (g.strategy == SRX_STRATEGY_FRAME_DISTANCE) {
+                const int fi = i / (g.h * g.w);
+                wgt = __fdiv_rn(1.f, (float)(abs(fi - fj) + 1));                   // algorithms.py:66-70
+            } else if (g.strategy == SRX_STRATEGY_PIXEL_DISTANCE) {
+                const int r = i % (g.h * g.w);
+                const int yi = b.down_y[r / g.w], xi = b.down_x[r % g.w];
+                wgt = __fdiv_rn(1.f, (float)(abs(xi - xj) + abs(yi - yj) + 1));    // algorithms.py:87-93
+            }
+            float *dst = b.sum + (long long)i * g.C;
+            if ((g.C & 3) == 0) {
+                for (int c = 0; c < g.C; c += 4)
+                    red_add_f32x4(dst + c, wgt * XIo<XT>::ld(xp + c * plane), wgt * XIo<XT>::ld(xp + (c + 1) * plane),
+                                  wgt * XIo<XT>::ld(xp + (c + 2) * plane), wgt * XIo<XT>::ld(xp + (c + 3) * plane));
+            } else {
+                for (int c = 0; c < g.C; ++c) red_add_f32(dst + c, wgt * XIo<XT>::ld(xp + c * plane));
+            }
+            red_add_f32(b.wsum + i, wgt);
+            red_add_f32(b.cnt + i, 1.f);
+        }
+    }
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(256) k_legacy_finalize(XT *__restrict__ x, LegacyBufs b, LegacyGeom g, float alpha,
+                                                          float one_minus, long long ncell) {
+    for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < ncell; cell += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(cell % ((long long)g.h * g.w));
+        const int f = (int)(cell / ((long long)g.h * g.w));
+        const bool mixed = b.cellslot[cell] >= 0 && b.cnt[cell] >= 2.f;  // traces of length 1 are skipped (overlap.py:123-127)
+        float denom = 1.f;
+        if (mixed) denom = g.strategy == SRX_STRATEGY_VIEW_NORMAL ? __fmul_rn(b.cnt[cell], b.wself[cell]) : b.wsum[cell];
+        for (int c = 0; c < g.C; ++c) {
+            const float xi = b.selfx[cell * g.C + c];
+            float out = xi;
+            if (mixed) {
+                const float ov = __fdiv_rn(b.sum[cell * g.C + c], denom);
+                out = __fadd_rn(__fmul_rn(alpha, ov), __fmul_rn(one_minus, xi));    // overlap.py:145
+            }
+            XT *p = x + ((long long)f * g.C + c) * g.h * g.w + r;
+            if (g.resize) {
+                if (out != 0.f) XIo<XT>::st(p, out);   // torch.where(ovlp != 0, ovlp, original), overlap.py:221
+            } else {
+                XIo<XT>::st(p, out);
+            }
+        }
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------
+struct LegacyLayout {
+    int64_t cap, ncell;
+    int64_t keys, head, next, cellslot, selfx, sum, wsum, cnt, wself, tables, status, total;
+    int64_t zero_begin, zero_end;  // [sum .. cnt] cleared per call
+};
+
+static inline int64_t lg_align(int64_t v) { return (v + 255) / 256 * 256; }
+
+static LegacyLayout legacy_layout(const srx_legacy_desc *d) {
+    LegacyLayout L;
+    L.ncell = (int64_t)d->frames * d->lat_h * d->lat_w;
+    int64_t cap = 1024;
+    while (cap < 2 * L.ncell) cap <<= 1;
+    L.cap = cap;
+    int64_t off = 0;
+    L.keys = off; off = lg_align(off + cap * 8);
+    L.head = off; off = lg_align(off + cap * 4);
+    L.next = off; off = lg_align(off + L.ncell * 4);
+    L.cellslot = off; off = lg_align(off + L.ncell * 4);
+    L.selfx = off; off = lg_align(off + L.ncell * d->channels * 4);
+    L.zero_begin = off;
+    L.sum = off; off = lg_align(off + L.ncell * d->channels * 4);
+    L.wsum = off; off = lg_align(off + L.ncell * 4);
+    L.cnt = off; off = lg_align(off + L.ncell * 4);
+    L.zero_end = off;
+    L.wself = off; off = lg_align(off + L.ncell * 4);
+    L.tables = off; off = lg_align(off + (int64_t)(d->height + d->width + d->lat_h + d->lat_w) * 4);
+    L.status = off; off += 256;
+    L.total = off;
+    return L;
+}
+
+static int legacy_validate(const srx_legacy_desc *d) {
+    SRX_REQUIRE(d, SRX_ERR_INVALID, "null descriptor");
+    SRX_REQUIRE(d->id_dtype == SRX_I32 || d->id_dtype == SRX_I16, SRX_ERR_INVALID, "id dtype must be int32 or int16");
+    SRX_REQUIRE(d->frames > 0 && d->height > 0 && d->width > 0 && d->channels > 0 && d->lat_h > 0 && d->lat_w > 0, SRX_ERR_INVALID, "non-positive dimension");
+    SRX_REQUIRE(d->strategy >= SRX_STRATEGY_AVERAGE && d->strategy <= SRX_STRATEGY_VIEW_NORMAL, SRX_ERR_INVALID, "Unknown algorithm %d", d->strategy);
+    SRX_REQUIRE((int64_t)d->frames * d->lat_h * d->lat_w < (1ll << 30), SRX_ERR_UNSUPPORTED, "too many latent cells for 32-bit chaining");
+    return SRX_OK;
+}
+
+extern "C" int64_t srx_legacy_workspace_bytes(const srx_legacy_desc *d) {
+    if (legacy_validate(d) != SRX_OK) return -1;
+    return legacy_layout(d).total;
+}
+
+// F.interpolate(mode='nearest') source index: min(floor(dst * fl32(in/out)), in-1)
+static void nearest_table(int *dst, int out_size, int in_size) {
+    volatile float scale = (float)in_size / (float)out_size;
+    for (int i = 0; i < out_size; ++i) {
+        volatile float v = (float)i * scale;
+        int s = (int)floorf(v);
+        dst[i] = s < in_size - 1 ? s : in_size - 1;
+    }
+}
+
+template <typename IdT, typename XT>
+static int legacy_impl(const srx_legacy_desc *d, const srx_legacy_args *a, cudaStream_t st) {
+    const LegacyLayout L = legacy_layout(d);
+    char *ws = reinterpret_cast<char *>(a->workspace_dev);
+    LegacyBufs b;
+    b.keys = reinterpret_cast<unsigned long long *>(ws + L.keys);
+    b.head = reinterpret_cast<int *>(ws + L.head);
+    b.next = reinterpret_cast<int *>(ws + L.next);
+    b.cellslot = reinterpret_cast<int *>(ws + L.cellslot);
+    b.selfx = reinterpret_cast<float *>(ws + L.selfx);
+    b.sum = reinterpret_cast<float *>(ws + L.sum);
+    b.wsum = reinterpret_cast<float *>(ws + L.wsum);
+    b.cnt = reinterpret_cast<float *>(ws + L.cnt);
+    b.wself = reinterpret_cast<float *>(ws + L.wself);
+    b.up_y = reinterpret_cast<int *>(ws + L.tables);
+    b.up_x = b.up_y + d->height;
+    b.down_y = b.up_x + d->width;
+    b.down_x = b.down_y + d->lat_h;
+    b.status = reinterpret_cast<int *>(ws + L.status);
+
+    std::vector<int> tab((size_t)d->height + d->width + d->lat_h + d->lat_w);
+    nearest_table(tab.data(), d->height, d->lat_h);                                   // up: id row -> latent row
+    nearest_table(tab.data() + d->height, d->width, d->lat_w);
+    nearest_table(tab.data() + d->height + d->width, d->lat_h, d->height);            // down: latent row -> id row
+    nearest_table(tab.data() + d->height + d->width + d->lat_h, d->lat_w, d->width);
+    SRX_CUDA_CHECK(cudaMemcpyAsync(b.up_y, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    SRX_CUDA_CHECK(cudaMemsetAsync(b.keys, 0xFF, (size_t)L.cap * 8, st));
+    SRX_CUDA_CHECK(cudaMemsetAsync(b.head, 0xFF, (size_t)L.cap * 4, st));
+    SRX_CUDA_CHECK(cudaMemsetAsync(ws + L.zero_begin, 0, (size_t)(L.zero_end - L.zero_begin), st));
+    SRX_CUDA_CHECK(cudaMemsetAsync(b.status, 0, 256, st));
+
+    LegacyGeom g;
+    g.T = d->frames; g.H = d->height; g.W = d->width; g.h = d->lat_h; g.w = d->lat_w; g.C = d->channels;
+    g.merge = d->merge_len > 1 ? d->merge_len : 1;
+    g.strategy = d->strategy;
+    g.resize = (d->lat_h != d->height || d->lat_w != d->width) ? 1 : 0;
+    g.mask = (unsigned int)(L.cap - 1);
+    const int sms = srx_sm_count_cached();
+    const long long npx = (long long)d->frames * d->height * d->width;
+    const IdT *ids = reinterpret_cast<const IdT *>(a->ids_dev);
+    XT *x = reinterpret_cast<XT *>(a->x_dev);
+    auto blocks = [&](long long n) { long long nb = (n + 255) / 256; return (int)(nb < (long long)sms * 8 ? (nb < 1 ? 1 : nb) : (long long)sms * 8); };
+    k_legacy_seed<IdT, XT><<<blocks(L.ncell), 256, 0, st>>>(ids, x, a->view_normal_dev, b, g, L.ncell);
+    k_legacy_accum<IdT, XT><<<blocks(npx), 256, 0, st>>>(ids, x, a->view_normal_dev, b, g, npx);
+    k_legacy_finalize<XT><<<blocks(L.ncell), 256, 0, st>>>(x, b, g, a->alpha, (float)(1.0 - (double)a->alpha), L.ncell);
+    SRX_CUDA_CHECK(cudaGetLastError());
+    int st_host = 0;
+    SRX_CUDA_CHECK(cudaMemcpyAsync(&st_host, b.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SRX_CUDA_CHECK(cudaStreamSynchronize(st));  // also keeps `tab` alive until the upload has been consumed
+    if (st_host)
+        return srx_set_error(SRX_ERR_KEY_RANGE, "an id component does not fit the packed 64-bit key "
+                             "(int32 ids: sprite, material < 1024, third component < 4096 after merge, fourth >= 0)");
+    return SRX_OK;
+}
+
+template <typename IdT>
+static int legacy_x_dispatch(const srx_legacy_desc *d, const srx_legacy_args *a, cudaStream_t st) {
+    switch (a->x_dtype) {
+        case SRX_F32: return legacy_impl<IdT, float>(d, a, st);
+        case SRX_F16: return legacy_impl<IdT, __half>(d, a, st);
+        case SRX_BF16: return legacy_impl<IdT, __nv_bfloat16>(d, a, st);
+        default: return srx_set_error(SRX_ERR_INVALID, "latent dtype must be f32/f16/bf16");
+    }
+}
+
+extern "C" int srx_legacy_overlap(const srx_legacy_desc *d, const srx_legacy_args *a, void *stream) {
+    int rc = legacy_validate(d);
+    if (rc) return rc;
+    SRX_REQUIRE(a && a->x_dev && a->ids_dev && a->workspace_dev, SRX_ERR_INVALID, "null buffer");
+    SRX_REQUIRE(d->strategy != SRX_STRATEGY_VIEW_NORMAL || a->view_normal_dev, SRX_ERR_INVALID,
+                "perpendicular_view_normal needs view_normal_map (algorithms.py:106)");
+    SRX_REQUIRE(a->workspace_bytes >= legacy_layout(d).total, SRX_ERR_INVALID, "workspace too small");
+    SRX_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace_dev) & 255) == 0, SRX_ERR_INVALID, "workspace must be 256-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return d->id_dtype == SRX_I32 ? legacy_x_dispatch<int4>(d, a, st) : legacy_x_dispatch<short4>(d, a, st);
+}

@@ -1,0 +1,12 @@
+"""Legacy-generation overlap API (reference: legacy_codes/stable_rendering_algo/{overlap,data_classes}):
+`Overlap`, `ResizeOverlap`, the four `OverlapAlgorithm` strategies, `Scheduler` and `CorrespondenceMap`."""
+from .algorithms import (AverageDistance, FrameDistance, OverlapAlgorithm, PerpendicularViewNormal, PixelDistance,
+                         overlap_algorithm_factory)
+from .correspondence import CorrespondenceMap
+from .driver import Overlap, ResizeOverlap
+from .scheduler import Scheduler, value_interpolation
+from .view_normal import build_view_normal_map
+
+__all__ = ["OverlapAlgorithm", "AverageDistance", "FrameDistance", "PixelDistance", "PerpendicularViewNormal",
+           "overlap_algorithm_factory", "CorrespondenceMap", "Overlap", "ResizeOverlap", "Scheduler",
+           "value_interpolation", "build_view_normal_map"]

@@ -1,0 +1,126 @@
+"""`Overlap` and `ResizeOverlap` (reference: legacy_codes/stable_rendering_algo/overlap/overlap.py:18-222).
+
+Same constructor and call signatures; one `srx_legacy_overlap` call replaces the per-vertex Python loop.
+kernel_radius > 0 is rejected: in the reference it is an in-place (Gauss–Seidel, dict-order dependent) update
+(overlap.py:97,136-145) that has no parallel definition — see DESIGN.md §6."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from .. import _lib
+from .algorithms import OverlapAlgorithm
+from .correspondence import CorrespondenceMap
+from .scheduler import Scheduler
+
+
+class Overlap:
+    def __init__(self, alpha_scheduler: Scheduler, kernel_radius_scheduler: Scheduler, algorithm: OverlapAlgorithm,
+                 verbose: bool = True):
+        self._verbose = verbose
+        self.algorithm = algorithm
+        self.alpha_scheduler = alpha_scheduler
+        self.kernel_radius_scheduler = kernel_radius_scheduler
+        self._workspace: Optional[torch.Tensor] = None
+
+    @property
+    def verbose(self):
+        return self._verbose
+
+    @verbose.setter
+    def verbose(self, value: bool):
+        self._verbose = value
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _run(self, stack: torch.Tensor, corr_map: CorrespondenceMap, alpha: float, view_normal_map) -> None:
+        """stack [T, B*C, h, w] contiguous CUDA tensor, updated in place."""
+        if not stack.is_cuda:
+            raise _lib.SrxUnavailable("latents must be CUDA tensors (there is no CPU path)")
+        lib = _lib.load()
+        strategy = getattr(self.algorithm, "strategy", None)
+        if strategy not in _lib.SRX_STRATEGY:
+            raise ValueError(f"Unknown algorithm {strategy}")
+        ids = corr_map.device_ids(stack.device)
+        T, CC, h, w = stack.shape
+        if ids.shape[0] < T:
+            raise ValueError(f"correspondence map has {ids.shape[0]} frames, latents {T}")
+        ids = ids[:T]
+        d = _lib.srx_legacy_desc()
+        d.id_dtype = _lib.torch_dtype_code(ids.dtype)
+        d.frames, d.height, d.width = T, ids.shape[1], ids.shape[2]
+        d.channels, d.lat_h, d.lat_w = CC, h, w
+        d.merge_len = corr_map.merge_len
+        d.strategy = _lib.SRX_STRATEGY[strategy]
+        need = int(lib.srx_legacy_workspace_bytes(C.byref(d)))
+        if need < 0:
+            _lib.check(_lib.SRX_ERR_INVALID)
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != stack.device:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=stack.device)
+        a = _lib.srx_legacy_args()
+        a.x_dev, a.x_dtype = stack.data_ptr(), _lib.torch_dtype_code(stack.dtype)
+        a.ids_dev = ids.data_ptr()
+        a.alpha = float(alpha)
+        vn = None
+        if strategy == "perpendicular_view_normal":
+            if view_normal_map is None:
+                raise TypeError("overlap() missing 1 required positional argument: 'view_normal_map'")
+            vn = view_normal_map.reshape(view_normal_map.shape[0], ids.shape[1], ids.shape[2])[:T]
+            vn = vn.to(device=stack.device, dtype=torch.float32).contiguous()
+            a.view_normal_dev = vn.data_ptr()
+        a.workspace_dev, a.workspace_bytes = self._workspace.data_ptr(), self._workspace.numel()
+        with torch.cuda.device(stack.device):
+            _lib.check(lib.srx_legacy_overlap(C.byref(d), C.byref(a), _lib.current_stream_ptr(stack.device)))
+
+    def _schedule(self, step, timestep):
+        alpha = self.alpha_scheduler(step, timestep)
+        radius = int(self.kernel_radius_scheduler(step, timestep))
+        if radius > 0:
+            raise NotImplementedError(
+                "kernel_radius > 0 is an order-dependent in-place update in the reference (overlap.py:97,136-145) "
+                "and is not supported; schedule the radius to 0")
+        return float(alpha)
+
+    @torch.no_grad()
+    def __call__(self, frame_seq: List[torch.Tensor], corr_map: CorrespondenceMap, step: int = None,
+                 timestep: int = None, apply_corr_map_decay: bool = False, **kwargs) -> torch.Tensor:
+        """frame_seq: T tensors [B,C,H,W] at the correspondence map's resolution -> stack [T,B,C,H,W] (overlap.py:83-152)."""
+        assert frame_seq[0].shape[2:] == (corr_map.height, corr_map.width), \
+            f"frame shape {frame_seq[0].shape[2:]} does not match corr_map shape {(corr_map.height, corr_map.width)}"
+        alpha = self._schedule(step, timestep)
+        stack = torch.stack(frame_seq, dim=0).contiguous()      # [T,B,C,H,W], a fresh tensor like the reference's
+        T, B, Cc, H, W = stack.shape
+        self._run(stack.view(T, B * Cc, H, W), corr_map, alpha, kwargs.get("view_normal_map"))
+        return stack
+
+
+class ResizeOverlap(Overlap):
+    def __init__(self, alpha_scheduler: Scheduler, kernel_radius_scheduler: Scheduler, algorithm: OverlapAlgorithm,
+                 verbose: bool = True, interpolate_mode: str = "nearest"):
+        super().__init__(alpha_scheduler, kernel_radius_scheduler, algorithm, verbose)
+        self._interpolate_mode = interpolate_mode
+
+    @property
+    def interpolate_mode(self):
+        return self._interpolate_mode
+
+    @interpolate_mode.setter
+    def interpolate_mode(self, value: str):
+        self._interpolate_mode = value
+
+    @torch.no_grad()
+    def __call__(self, frame_seq: List[torch.Tensor], corr_map: CorrespondenceMap, step: int = None,
+                 timestep: int = None, **kwargs) -> List[torch.Tensor]:
+        """frame_seq: T latents [B,C,h,w]; returns T overlapped latents (overlap.py:180-222).  The up-sample /
+        overlap / down-sample / where() chain is evaluated directly on the latent cells."""
+        alpha = self.alpha_scheduler(step, timestep)
+        if alpha == 0:
+            return frame_seq                                    # overlap.py:200-201
+        if self._interpolate_mode != "nearest":
+            raise NotImplementedError("only interpolate_mode='nearest' (the reference default) is supported")
+        alpha = self._schedule(step, timestep)
+        stack = torch.stack(frame_seq, dim=0).contiguous()      # [T,B,C,h,w]
+        T, B, Cc, h, w = stack.shape
+        self._run(stack.view(T, B * Cc, h, w), corr_map, alpha, kwargs.get("view_normal_map"))
+        return [stack[i] for i in range(T)]

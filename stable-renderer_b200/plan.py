@@ -1,0 +1,126 @@
+"""OverlapPlan — thin owner of an `srx_plan` handle plus its torch-allocated workspace.
+
+One plan serves one batch of id buffers (one `IDMap`) and one latent shape; it is what the reference caches as
+`IDMap._vertex_screen_info_cache` (source/engine/static/corrmap.py:218-280), except that nothing per-entry is
+materialised: keying happens inside the streaming kernel."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+class OverlapPlan:
+    def __init__(self, ids: Optional[torch.Tensor], latent_shape: Sequence[int], *,
+                 frame_indices: Optional[Sequence[int]] = None, id_shape: Optional[Sequence[int]] = None,
+                 id_dtype: Optional[torch.dtype] = None, key_capacity: int = 0, deterministic: bool = False,
+                 device: Optional[torch.device] = None):
+        lib = _lib.load()
+        if ids is not None:
+            if not ids.is_cuda:
+                raise _lib.SrxUnavailable("id buffers must live on a CUDA device (there is no CPU path)")
+            if ids.dim() != 4 or ids.shape[-1] != 4:
+                raise ValueError(f"id buffers must be [F,H,W,4], got {tuple(ids.shape)}")
+            ids = ids.contiguous()
+            id_shape, id_dtype, device = ids.shape, ids.dtype, ids.device
+        elif id_shape is None or id_dtype is None or key_capacity <= 0 or device is None:
+            raise ValueError("without ids, id_shape, id_dtype, device and key_capacity are required")
+        F, H, W = int(id_shape[0]), int(id_shape[1]), int(id_shape[2])
+        B, Cc, h, w = (int(v) for v in latent_shape)
+        self.device = torch.device(device)
+        self.id_shape = (F, H, W, 4)
+        self.id_dtype = id_dtype
+        self.latent_shape = (B, Cc, h, w)
+        self.deterministic = bool(deterministic)
+        self._ids = ids
+        desc = _lib.srx_plan_desc()
+        desc.id_dtype = _lib.torch_dtype_code(id_dtype)
+        desc.frames, desc.height, desc.width = F, H, W
+        desc.batch, desc.channels, desc.lat_h, desc.lat_w = B, Cc, h, w
+        desc.key_mode = _lib.SRX_KEY_VERTEX
+        desc.merge_len = 0
+        desc.accum_mode = _lib.SRX_ACCUM_DETERMINISTIC if deterministic else _lib.SRX_ACCUM_FAST
+        desc.key_capacity = int(key_capacity)
+        fm = None
+        if frame_indices is not None:
+            if len(frame_indices) != F:
+                raise ValueError(f"frame_indices has {len(frame_indices)} entries for {F} id frames")
+            fm = (C.c_int32 * F)(*[int(v) for v in frame_indices])
+            desc.frame_map = C.cast(fm, C.POINTER(C.c_int32))
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            stream = _lib.current_stream_ptr(self.device)
+            _lib.check(lib.srx_plan_create(C.byref(self._handle), C.byref(desc), ids.data_ptr() if ids is not None else None,
+                                           stream))
+            info = _lib.srx_plan_info()
+            _lib.check(lib.srx_plan_get_info(self._handle, C.byref(info)))
+            self.info = info
+            self.workspace = torch.empty(int(info.workspace_bytes), dtype=torch.uint8, device=self.device)
+            _lib.check(lib.srx_plan_bind_workspace(self._handle, self.workspace.data_ptr(), int(info.workspace_bytes), stream))
+        self.key_capacity = int(info.key_capacity)
+        self.n_valid = int(info.n_valid)
+        self.fast_path = bool(info.fast_path)
+
+    # -- accumulator view for the multi-GPU exchange ---------------------------------------
+    @property
+    def accumulator(self) -> torch.Tensor:
+        """The key-indexed accumulator [K*(C+1)] (float32; int64 in deterministic mode): K*C sums then K counts."""
+        dt = torch.int64 if self.deterministic else torch.float32
+        raw = self.workspace[int(self.info.accum_offset): int(self.info.accum_offset + self.info.accum_bytes)]
+        return raw.view(dt)
+
+    def _args(self, x: torch.Tensor, ids: Optional[torch.Tensor], ratio: float, adain: bool,
+              need_ids: bool = True) -> _lib.srx_step_args:
+        if tuple(x.shape) != self.latent_shape:
+            raise ValueError(f"latents {tuple(x.shape)} do not match the plan {self.latent_shape}")
+        if not x.is_cuda or x.device != self.device:
+            raise _lib.SrxUnavailable("latents must live on the plan's CUDA device (there is no CPU path)")
+        if not x.is_contiguous():
+            raise ValueError("latents must be contiguous")
+        a = _lib.srx_step_args()
+        a.x_dev = x.data_ptr()
+        a.x_dtype = _lib.torch_dtype_code(x.dtype)
+        a.ids_dev = None
+        if need_ids:
+            ids = self._ids if ids is None else ids
+            if ids is None:
+                raise ValueError("this plan was built without ids: pass them to every call")
+            if (tuple(ids.shape) != self.id_shape or ids.dtype != self.id_dtype or ids.device != self.device
+                    or not ids.is_contiguous()):
+                raise ValueError("id buffers do not match the plan (shape / dtype / device / contiguity)")
+            a.ids_dev = ids.data_ptr()
+        a.ratio = float(ratio)
+        a.adain = 1 if adain else 0
+        a.cache_slots = 0
+        return a
+
+    def step(self, x: torch.Tensor, ratio: float, *, adain: bool = True, ids: Optional[torch.Tensor] = None) -> None:
+        """One overlap step in place on x (reduce + gather on this GPU)."""
+        a = self._args(x, ids, ratio, adain)
+        _lib.check(_lib.load().srx_overlap_step(self._handle, C.byref(a), _lib.current_stream_ptr(self.device)))
+
+    def reduce(self, x: torch.Tensor, *, ids: Optional[torch.Tensor] = None) -> None:
+        a = self._args(x, ids, 0.0, True)
+        _lib.check(_lib.load().srx_accum_reduce(self._handle, C.byref(a), _lib.current_stream_ptr(self.device)))
+
+    def gather(self, x: torch.Tensor, ratio: float, *, adain: bool = True) -> None:
+        a = self._args(x, None, ratio, adain, need_ids=False)
+        _lib.check(_lib.load().srx_accum_finalize_gather(self._handle, C.byref(a), _lib.current_stream_ptr(self.device)))
+
+    def check(self) -> None:
+        """Raises for device-side failures of earlier launches (syncs)."""
+        _lib.check(_lib.load().srx_plan_check(self._handle, _lib.current_stream_ptr(self.device)))
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None) is not None and self._handle:
+            _lib.load().srx_plan_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,111 @@
+"""-m gpu: CorrespondMap.update on the GPU vs reference-generated fixtures (bit-exact fp16 atlas + written flags)."""
+import numpy as np
+import pytest
+import torch
+
+import srx_oracle as O
+from helpers import EngineData, assert_close, t2n
+
+pytestmark = pytest.mark.gpu
+
+
+def _atlas(cm):
+    return cm._values.cpu().numpy().view(np.uint16), cm._writtens.cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", ["first", "replace", "first_avg", "replace_avg"])
+def test_bake_masked_bit_exact(golden, mode):
+    from stable_renderer_b200.corrmap import CorrespondMap
+    g = golden(f"bake_{mode}_masked")
+    k, tex = int(g["k"]), int(g["tex"])
+    cm = CorrespondMap(name="t", k=k, height=tex, width=tex, channel_count=4)
+    cm.update(torch.from_numpy(g["colors"]), torch.from_numpy(g["ids"]), spriteID=1, materialID=0, mode=mode,
+              masks=torch.from_numpy(g["masks"]), inverse_masks=True, ignore_obj_mat_id=True)
+    v, w = _atlas(cm)
+    assert np.array_equal(w, g["writtens"])
+    assert np.array_equal(v, g["values"].view(np.uint16))
+
+
+def test_bake_first_two_calls_sprite_filter(golden):
+    from stable_renderer_b200.corrmap import CorrespondMap
+    g = golden("bake_first_sprite2_two_calls")
+    k, tex = int(g["k"]), int(g["tex"])
+    cm = CorrespondMap(name="t", k=k, height=tex, width=tex, channel_count=4)
+    colors, ids = torch.from_numpy(g["colors"]).cuda(), torch.from_numpy(g["ids"]).cuda()
+    cm.update(colors[:2], ids[:2], spriteID=2, materialID=0, mode="first")
+    cm.update([c for c in colors[2:]], [i for i in ids[2:]], spriteID=2, materialID=0, mode="first")   # list-of-frames form
+    v, w = _atlas(cm)
+    assert np.array_equal(w, g["writtens"])
+    assert np.array_equal(v, g["values"].view(np.uint16))
+
+
+def test_bake_through_default_corresponder_finished(golden):
+    from stable_renderer_b200.corresponder import DefaultCorresponder
+    from stable_renderer_b200.corrmap import CorrespondMap, IDMap
+    g = golden("bake_finished_replace_c3")
+    k, tex = int(g["k"]), int(g["tex"])
+    cm = CorrespondMap(name="t", k=k, height=tex, width=tex, channel_count=3)
+    dc = DefaultCorresponder(update_corrmap_mode="replace", ignore_obj_mat_id_when_update=True)
+    ed = EngineData(IDMap(tensor=torch.from_numpy(g["ids"]).cuda()), {(1, 0): cm})
+    dc.finished(ed, torch.from_numpy(g["colors"]).cuda())
+    v, w = _atlas(cm)
+    assert np.array_equal(w, g["writtens"])
+    assert np.array_equal(v, g["values"].view(np.uint16))
+    dc2 = DefaultCorresponder(update_corrmap=False)
+    cm2 = CorrespondMap(name="t2", k=k, height=tex, width=tex, channel_count=3)
+    dc2.finished(EngineData(ed.id_maps, {(1, 0): cm2}), torch.from_numpy(g["colors"]).cuda())
+    assert not cm2._writtens.any()
+
+
+@pytest.mark.parametrize("mode", ["first", "replace"])
+def test_bake_vs_oracle_bigger(mode):
+    """256^2 views into a k=3 128^2 atlas, fp16 and bf16 colours, sprite filter + masks together (the consistent
+    definition)."""
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import CorrespondMap
+    F, H, tex, k = 6, 256, 128, 3
+    ids = synthetic.make_ids(F, H, H, tex_h=tex, tex_w=tex, k=k, n_obj=2, frac_2048=0.05, seed=3)
+    colors = synthetic.make_colors(F, H, H, 3, seed=4)
+    masks = torch.from_numpy(O.idmap_masks(ids.numpy()))
+    for dt in (torch.float32, torch.float16, torch.bfloat16):
+        col = colors.to(dt)
+        values, writtens = O.corrmap_new(k, tex, tex, 4)
+        O.corrmap_update(values, writtens, col.float().numpy(), ids.numpy(), spriteID=2, materialID=0, mode=mode,
+                         masks=masks.numpy(), inverse_masks=True)
+        cm = CorrespondMap(name="t", k=k, height=tex, width=tex, channel_count=4)
+        cm.update(col, ids, spriteID=2, materialID=0, mode=mode, masks=masks, inverse_masks=True)
+        v, w = _atlas(cm)
+        assert np.array_equal(w, writtens)
+        assert np.array_equal(v, values.view(np.uint16))
+
+
+def test_bake_index_error_and_bad_args():
+    from stable_renderer_b200.corrmap import CorrespondMap
+    cm = CorrespondMap(name="t", k=1, height=4, width=4, channel_count=4)
+    ids = torch.zeros(1, 2, 2, 4, dtype=torch.int32)
+    ids[..., 2] = 2048
+    with pytest.raises(IndexError):      # verified reference behaviour without masks
+        cm.update(torch.zeros(1, 2, 2, 3), ids, mode="replace")
+    with pytest.raises(ValueError):
+        cm.update(torch.zeros(2, 2, 2, 3), torch.zeros(1, 2, 2, 4, dtype=torch.int32))
+    with pytest.raises(ValueError):
+        cm.update(torch.zeros(1, 2, 2, 3), torch.zeros(1, 2, 2, 4, dtype=torch.int32), mode="bogus")
+
+
+@pytest.mark.parametrize("weight_mode", ["uniform", "view_normal", "view_normal_depth"])
+def test_weighted_multi_view_bake_vs_oracle(weight_mode):
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import CorrespondMap
+    F, H, tex, k = 8, 128, 64, 2
+    ids = synthetic.make_ids(F, H, H, tex_h=tex, tex_w=tex, k=k, frac_2048=0.05, seed=8)
+    colors = synthetic.make_colors(F, H, H, 3, seed=5)
+    nd = synthetic.make_normal_depth(F, H, H, seed=2)
+    acc = np.zeros((k * k, tex * tex, 4)); wsum = np.zeros((k * k, tex * tex))
+    O.corrmap_update_weighted(acc, wsum, colors.numpy(), ids.numpy(), nd.float().numpy(), weight_mode, spriteID=1)
+    values, writtens = O.corrmap_new(k, tex, tex, 4)
+    O.corrmap_finalize_weighted(values, writtens, acc, wsum)
+    cm = CorrespondMap(name="t", k=k, height=tex, width=tex, channel_count=4)
+    cm.update(colors, ids, spriteID=1, mode="replace", weight_mode=weight_mode, normal_depth=nd)
+    assert np.array_equal(cm._writtens.cpu().numpy(), writtens)
+    # float32 atomics vs float64 sums, then one fp16 rounding: allow one fp16 ulp (2^-11 relative)
+    assert_close(t2n(cm._values), values.astype(np.float32), 1e-3, 1e-6, weight_mode)

@@ -156,3 +156,31 @@ def test_legacy_scheduler_table(golden):
                                 end_timestep=900, interpolate_begin=0.9, interpolate_end=0.2, power=power,
                                 interpolate_type=names[int(itype)], no_interpolate_return=0.05)
         assert got == pytest.approx(want, rel=1e-12, abs=1e-15)
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_torch_port_matches_reference(golden, name):
+    """oracle/torch_port.py (bench.py's CPU baseline) against the same reference-generated fixtures."""
+    import torch
+    from torch_port import CpuOverlapPort
+    g = golden(name)
+    torch.set_num_threads(1)     # index_put_ with duplicate indices is only ordered with one thread
+    port = CpuOverlapPort(torch.from_numpy(g["ids"]), [int(v) for v in g["frame_indices"]])
+    assert port.n_entries == g["vsi"].shape[0]
+    out = port.step(torch.from_numpy(g["x"]), float(g["ratio"]))
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=1e-5, atol=2e-6)
+
+
+def test_torch_bake_port_matches_reference(golden):
+    import torch
+    from torch_port import cpu_bake_port
+    torch.set_num_threads(1)
+    for mode in ("first", "replace"):
+        g = golden(f"bake_{mode}_masked")
+        k, tex = int(g["k"]), int(g["tex"])
+        values = torch.zeros(k * k, tex * tex, 4, dtype=torch.float16)
+        writtens = torch.zeros(k * k, tex * tex, dtype=torch.bool)
+        cpu_bake_port(values, writtens, torch.from_numpy(g["colors"]), torch.from_numpy(g["ids"]),
+                      torch.from_numpy(g["masks"]), mode)
+        assert np.array_equal(writtens.numpy(), g["writtens"])
+        assert np.array_equal(values.numpy().view(np.uint16), g["values"].view(np.uint16))
