@@ -53,6 +53,20 @@ __device__ __forceinline__ IdPx load_id(const short4 *p) {
     return IdPx{(int)(short)(lo & 0xffff), (int)(short)(lo >> 16), (int)(short)(hi & 0xffff), (int)(short)(hi >> 16)};
 }
 
+// Two horizontally adjacent id pixels with one load.  RGBA_32I ids use Blackwell's 256-bit global load, streamed past
+// L1 and marked evict-first in L2 (each pixel is read exactly once; the accumulator and the latents should stay
+// resident instead).  The address must be 32-byte aligned (even pixel index).
+__device__ __forceinline__ void load_id_pair(const int4 *p, IdPx &a, IdPx &b) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.s), "=r"(a.m), "=r"(a.i), "=r"(a.v), "=r"(b.s), "=r"(b.m), "=r"(b.i), "=r"(b.v) : "l"(p));
+}
+__device__ __forceinline__ void load_id_pair(const short4 *p, IdPx &a, IdPx &b) {
+    int w0, w1, w2, w3;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "l"(p));
+    a = IdPx{(int)(short)(w0 & 0xffff), (int)(short)(w0 >> 16), (int)(short)(w1 & 0xffff), (int)(short)(w1 >> 16)};
+    b = IdPx{(int)(short)(w2 & 0xffff), (int)(short)(w2 >> 16), (int)(short)(w3 & 0xffff), (int)(short)(w3 >> 16)};
+}
+
 // corrmap.py:266-275 — keep rows with map_index != 2048 that are not all-zero
 __device__ __forceinline__ bool id_valid(const IdPx &p) {
     return (p.i != SRX_NO_ID_MAP_INDEX) && ((p.s | p.m | p.i | p.v) != 0);

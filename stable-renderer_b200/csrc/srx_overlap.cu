@@ -121,86 +121,133 @@ __global__ void __launch_bounds__(256) k_scan_ids(const IdT *__restrict__ ids, c
 // =================================================================================================================
 enum { ST_KEY_RANGE = 0, ST_CELL_RANGE = 1 };
 
+// Work item = 8 id rows x (8*U cells).  Each of the CTA's 8 warps owns U consecutive cells.  A lane holds two
+// horizontally adjacent pixels of a cell (one 256-bit load: lane = row*4 + pair, so lane order is the row-major pixel
+// order of the cell) and issues the loads of all U cells plus the cells' latents before consuming any: 4 KB of ids in
+// flight per warp, and the latent loads (which do not depend on the ids) overlap with them.
+// Reduce-by-key inside the warp uses no shuffles or match instructions: REDUX min/max detect a cell whose valid pixels
+// all share one key (one reduction for the whole cell); otherwise equal pixel pairs are merged in-lane.  The winner
+// (last valid pixel in row-major order) is a REDUX max over (position, slot) packed in 32 bits.
+#define K1_U 4
+#define SRX_SLOT_BITS 25   // dense slot limit 2^25: leaves 7 bits for (pixel position + 1) in the packed winner word
+
 template <typename IdT, typename XT, bool DET, bool FROM_SLOTS, bool WRITE_SLOTS>
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, 3)
 k_accum_r8(const IdT *__restrict__ ids, int *__restrict__ slotmap, const XT *__restrict__ x,
            const int *__restrict__ fmap, void *__restrict__ accum, int *__restrict__ winner, int *__restrict__ status,
-           int H, int W, int h, int w, long long kcap, long long ncells) {
+           int H, int W, int h, int w, long long kcap, int nrows, int chunks_per_row) {
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int r = lane >> 3, c = lane & 7;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = lane >> 2, pr = lane & 3;
     float *acc_f = reinterpret_cast<float *>(accum);
     float *cnt_f = acc_f + kcap * 4;
     long long *acc_q = reinterpret_cast<long long *>(accum);
     long long *cnt_q = acc_q + kcap * 4;
+    const int plane = h * w;
+    const int nitems = nrows * chunks_per_row;
 
-    for (long long ci = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < ncells; ci += nwarps) {
-        const int sx = (int)(ci % w);
-        const long long t = ci / w;
-        const int sy = (int)(t % h);
-        const int g = (int)(t / h);
-        const long long px0 = ((long long)g * H + sy * 8 + r) * W + sx * 8 + c;  // rows 0-3 of the cell
-        const long long px1 = px0 + 4LL * W;                                      // rows 4-7
-        int k0, k1;  // slot, or a per-lane unique negative sentinel for "no entry"
-        if (FROM_SLOTS) {
-            k0 = __ldg(slotmap + px0);
-            k1 = __ldg(slotmap + px1);
-        } else {
-            IdPx p0 = load_id(ids + px0);
-            IdPx p1 = load_id(ids + px1);
-            long long s0 = id_valid(p0) ? vertex_slot(p0.v) : -1;
-            long long s1 = id_valid(p1) ? vertex_slot(p1.v) : -1;
-            if ((s0 >= kcap) | (s1 >= kcap) | (id_valid(p0) & (s0 < 0)) | (id_valid(p1) & (s1 < 0))) {
-                atomicOr(status + ST_KEY_RANGE, 1);
-                if (s0 >= kcap) s0 = -1;
-                if (s1 >= kcap) s1 = -1;
-            }
-            k0 = s0 < 0 ? -1 : (int)s0;
-            k1 = s1 < 0 ? -1 : (int)s1;
-            if (WRITE_SLOTS) {
-                slotmap[px0] = k0;
-                slotmap[px1] = k1;
-            }
-        }
-        const unsigned b0 = __ballot_sync(FULL, k0 >= 0);
-        const unsigned b1 = __ballot_sync(FULL, k1 >= 0);
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int row = item / chunks_per_row;
+        const int chunk = item - row * chunks_per_row;
+        const int g = row / h;
+        const int sy = row - g * h;
         const int fl = fmap[g];
-        int win = -1;
-        if (b0 | b1) {
-            // the cell's latent: lanes 0-3 fetch one channel each (L2 resident), then broadcast
-            float xv = 0.f;
-            if (lane < 4) xv = XIo<XT>::ld(x + (((long long)fl * 4 + lane) * h + sy) * w + sx);
-            const float x0 = __shfl_sync(FULL, xv, 0), x1 = __shfl_sync(FULL, xv, 1);
-            const float x2 = __shfl_sync(FULL, xv, 2), x3 = __shfl_sync(FULL, xv, 3);
-            // reduce-by-key inside the warp: lanes holding the same slot elect one leader that carries the multiplicity
-            const unsigned m0 = __match_any_sync(FULL, k0 >= 0 ? k0 : -1 - lane);
-            const unsigned m1 = __match_any_sync(FULL, k1 >= 0 ? k1 : -1 - lane);
+        const int sx0 = chunk * (8 * K1_U) + warp * K1_U;
+        const long long px_base = ((long long)g * H + sy * 8 + r) * W + pr * 2;   // pixel pair (row r, cols 2pr, 2pr+1) of cell 0
+        const XT *xrow = x + ((long long)fl * 4 * h + sy) * w;                   // channel 0 of this cell row
+        int *wrow = winner + ((long long)fl * h + sy) * w;
+
+        int ka[K1_U], kb[K1_U];   // slot of the lane's two pixels, -1 = no entry
+        float xv[K1_U][4];
+        if (FROM_SLOTS) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int k = half ? k1 : k0;
-                const unsigned m = half ? m1 : m0;
-                if (k >= 0 && lane == __ffs(m) - 1) {
-                    const int mult = __popc(m);
-                    if (DET) {
-                        const long long q = (long long)mult;
-                        red_add_s64(acc_q + (long long)k * 4 + 0, q * to_fix(x0));
-                        red_add_s64(acc_q + (long long)k * 4 + 1, q * to_fix(x1));
-                        red_add_s64(acc_q + (long long)k * 4 + 2, q * to_fix(x2));
-                        red_add_s64(acc_q + (long long)k * 4 + 3, q * to_fix(x3));
-                        red_add_s64(cnt_q + k, q);
-                    } else {
-                        const float fm = (float)mult;
-                        red_add_f32x4(acc_f + (long long)k * 4, fm * x0, fm * x1, fm * x2, fm * x3);
-                        red_add_f32(cnt_f + k, fm);
-                    }
+            for (int u = 0; u < K1_U; ++u) {
+                const int sx = sx0 + u;
+                ka[u] = kb[u] = -1;
+                if (sx < w) {
+                    const int2 v = __ldg(reinterpret_cast<const int2 *>(slotmap + px_base + sx * 8));
+                    ka[u] = v.x;
+                    kb[u] = v.y;
                 }
             }
-            // last valid pixel in row-major order of the cell: rows 4-7 (second load) come after rows 0-3
-            if (b1) win = __shfl_sync(FULL, k1, 31 - __clz(b1));
-            else win = __shfl_sync(FULL, k0, 31 - __clz(b0));
+        } else {
+            IdPx pa[K1_U], pb[K1_U];
+#pragma unroll
+            for (int u = 0; u < K1_U; ++u) {
+                const int sx = sx0 + u;
+                pa[u] = IdPx{0, 0, 0, 0};
+                pb[u] = IdPx{0, 0, 0, 0};
+                if (sx < w) load_id_pair(ids + px_base + sx * 8, pa[u], pb[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < K1_U; ++u) {
+                const bool va = id_valid(pa[u]), vb = id_valid(pb[u]);
+                long long sa = va ? vertex_slot(pa[u].v) : -1;
+                long long sb = vb ? vertex_slot(pb[u].v) : -1;
+                if ((sa >= kcap) | (sb >= kcap) | (va & (sa < 0)) | (vb & (sb < 0))) {
+                    atomicOr(status + ST_KEY_RANGE, 1);
+                    if (sa >= kcap) sa = -1;
+                    if (sb >= kcap) sb = -1;
+                }
+                ka[u] = sa < 0 ? -1 : (int)sa;
+                kb[u] = sb < 0 ? -1 : (int)sb;
+                if (WRITE_SLOTS && sx0 + u < w)
+                    *reinterpret_cast<int2 *>(slotmap + px_base + (sx0 + u) * 8) = make_int2(ka[u], kb[u]);
+            }
         }
-        if (lane == 0) winner[((long long)fl * h + sy) * w + sx] = win;
+        // the cells' latents: every lane reads the same 4 addresses (one L1/L2 transaction each, no shuffles)
+#pragma unroll
+        for (int u = 0; u < K1_U; ++u) {
+            const int sx = min(sx0 + u, w - 1);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) xv[u][ch] = XIo<XT>::ld(xrow + ch * plane + sx);
+        }
+
+#pragma unroll
+        for (int u = 0; u < K1_U; ++u) {
+            const int sx = sx0 + u;
+            if (sx >= w) break;   // warp-uniform
+            const int a = ka[u], b = kb[u];
+            const int nvalid = (a >= 0) + (b >= 0);
+            // winner: highest (pixel position, slot); positions 2*lane (a) and 2*lane+1 (b), stored +1 so that 0 = none
+            unsigned wpack = 0;
+            if (b >= 0) wpack = ((unsigned)(2 * lane + 2) << SRX_SLOT_BITS) | (unsigned)b;
+            else if (a >= 0) wpack = ((unsigned)(2 * lane + 1) << SRX_SLOT_BITS) | (unsigned)a;
+            wpack = __reduce_max_sync(FULL, wpack);
+            if (lane == 0) wrow[sx] = wpack ? (int)(wpack & ((1u << SRX_SLOT_BITS) - 1)) : -1;
+            if (wpack == 0) continue;   // no valid pixel in this cell (warp-uniform)
+            const int lo = __reduce_min_sync(FULL, min(a >= 0 ? a : INT_MAX, b >= 0 ? b : INT_MAX));
+            const int hi = __reduce_max_sync(FULL, max(a, b));
+            int k_red[2], m_red[2];   // up to two reductions from this lane
+            k_red[0] = k_red[1] = -1;
+            m_red[0] = m_red[1] = 0;
+            if (lo == hi) {           // every valid pixel of the cell carries the same key: one reduction for the cell
+                const int total = __reduce_add_sync(FULL, nvalid);
+                if (lane == 0) { k_red[0] = lo; m_red[0] = total; }
+            } else if (a >= 0 && a == b) {
+                k_red[0] = a; m_red[0] = 2;
+            } else {
+                k_red[0] = a; m_red[0] = 1;
+                k_red[1] = b; m_red[1] = 1;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int k = k_red[j];
+                if (k < 0) continue;
+                if (DET) {
+                    const long long q = (long long)m_red[j];
+                    red_add_s64(acc_q + (long long)k * 4 + 0, q * to_fix(xv[u][0]));
+                    red_add_s64(acc_q + (long long)k * 4 + 1, q * to_fix(xv[u][1]));
+                    red_add_s64(acc_q + (long long)k * 4 + 2, q * to_fix(xv[u][2]));
+                    red_add_s64(acc_q + (long long)k * 4 + 3, q * to_fix(xv[u][3]));
+                    red_add_s64(cnt_q + k, q);
+                } else {
+                    const float fm = (float)m_red[j];
+                    red_add_f32x4(acc_f + (long long)k * 4, fm * xv[u][0], fm * xv[u][1], fm * xv[u][2], fm * xv[u][3]);
+                    red_add_f32(cnt_f + k, fm);
+                }
+            }
+        }
     }
 }
 
@@ -545,10 +592,10 @@ extern "C" int srx_plan_create(srx_plan **out, const srx_plan_desc *desc, const 
         }
         p->kcap = p->key_max + 1 > 1 ? p->key_max + 1 : 1;
     }
-    if (p->kcap > (1ll << 27)) {
+    if (p->kcap > (1ll << SRX_SLOT_BITS)) {
         int64_t k = p->kcap;
         cudaFree(p->tables); delete p;
-        return srx_set_error(SRX_ERR_KEY_RANGE, "key capacity %lld exceeds the dense slot table limit 2^27", (long long)k);
+        return srx_set_error(SRX_ERR_KEY_RANGE, "key capacity %lld exceeds the dense slot table limit 2^25", (long long)k);
     }
     p->kcap = align_up(p->kcap, 64);
     plan_layout(p);
@@ -618,11 +665,12 @@ static int launch_accum(srx_plan *p, const srx_step_args *a, cudaStream_t st) {
     const XT *x = reinterpret_cast<const XT *>(a->x_dev);
     const IdT *ids = reinterpret_cast<const IdT *>(a->ids_dev);
     if (p->fast_r8) {
-        const long long ncells = (long long)d.frames * d.lat_h * d.lat_w;
+        const int nrows = d.frames * d.lat_h;
+        const int chunks = (d.lat_w + 8 * K1_U - 1) / (8 * K1_U);
         auto kern = k_accum_r8<IdT, XT, DET, false, false>;
-        const int grid = grid_for((const void *)kern, 256, 0, (ncells + 7) / 8);
+        const int grid = grid_for((const void *)kern, 256, 0, (long long)nrows * chunks);
         kern<<<grid, 256, 0, st>>>(ids, nullptr, x, p->fmap, accum, winner, status, d.height, d.width, d.lat_h, d.lat_w,
-                                   p->kcap, ncells);
+                                   p->kcap, nrows, chunks);
     } else {
         const long long npx = (long long)d.frames * d.height * d.width;
         const long long ncell_lat = (long long)d.batch * d.lat_h * d.lat_w;
