@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""bench.py — overlap-steps/s (and latent-px/s) of the correspondence-map latent overlap step on N B200s.
+"""bench.py — latent-px/s (and overlap-steps/s) of the correspondence-map latent overlap step on N B200s.
+
+`value` is the whole-job aggregate latent-px/s = (frames over all GPUs) * h * w * steps/s — the one of BASELINE.json's
+two metrics that adds up over GPUs; `overlap_steps_per_sec` is reported beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
@@ -316,7 +319,8 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
     clocks = sampler.stop()
 
     out = {
-        "metric": "overlap_steps_per_sec", "value": 1e3 / ms_step, "unit": "steps/s", "n_gpus": world, "steps": K,
+        "metric": "overlap_latent_px_per_sec", "value": F_global * h * h * 1e3 / ms_step, "unit": "latent-px/s",
+        "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": DTYPE_NAME[dtype], "data": "synthetic",
         "config": {"workload": f"{args.workload}: {F_global} frames of {H}x{H}x4 int32 ids -> {h}x{h}x4 "
@@ -326,11 +330,12 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
                    "l2": f"{n_rot} id buffers of {id_bytes >> 20} MiB rotate, so no step finds its ids in the 126 MB L2",
                    "parallelism": f"frames sharded over {world} GPU(s), NCCL all-reduce of the key accumulator "
                                   f"({acc.numel() * 4 >> 10} KiB)" if world > 1 else "single GPU"},
-        "latent_px_per_sec": F_global * h * h * 1e3 / ms_step,
+        "overlap_steps_per_sec": 1e3 / ms_step,
         "id_px_per_sec": F_global * H * H * 1e3 / ms_step,
         "clocks": clocks,
-        "e2e": {"value": 1e3 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": id_bytes + x.numel() * elem,
-                "d2h_bytes_per_step": x.numel() * elem, "ms_per_step": e2e_ms, "steps": n_e2e,
+        "e2e": {"value": F_global * h * h * 1e3 / e2e_ms, "unit": "latent-px/s",
+                "h2d_bytes_per_step": id_bytes + x.numel() * elem, "d2h_bytes_per_step": x.numel() * elem,
+                "ms_per_step": e2e_ms, "steps_per_sec": 1e3 / e2e_ms, "steps": n_e2e,
                 "api": "OverlapCorresponder.step_finished(engine_data, sampling_context)"},
         "gpu_launches": 2 * K if plan.fast_path else 3 * K,
         "roofline": {"bound": "hbm", "kernel": "k_accum_r8 (id-streaming key/segment-reduce pass)",
@@ -366,7 +371,8 @@ def cpu_overlap_baseline(workload: str, budget_s: float, max_steps: int, frames_
         times.append(time.perf_counter() - t0)
     t_step = statistics.median(times)
     scale = frames_cfg / F                                          # per-entry work is linear in the frame count
-    return {"value": 1.0 / (t_step * scale), "unit": "steps/s", "cores": cores, "kind": "port",
+    return {"value": frames_cfg * h * h / (t_step * scale), "unit": "latent-px/s", "steps_per_sec": 1.0 / (t_step * scale),
+            "cores": cores, "kind": "port",
             "sample": f"{len(times)} timed steps of {F}/{frames_cfg} frames of {workload} (median {t_step * 1e3:.1f} ms/step"
                       f"{', scaled by frame count' if F != frames_cfg else ''}); keying cached as in the reference "
                       f"(plan build {t_plan * 1e3:.0f} ms, excluded); torch {torch.__version__} CPU ops, {cores} threads",
@@ -447,14 +453,16 @@ def main():
         res = cpu_overlap_baseline(wl, budget_s=1e9, max_steps=args.steps, frames_cap=frames_cap)
         world = max(args.gpus, 1)
         frames_total = frames_cfg * world if scaling == "weak" else frames_cfg
-        value = res["value"] * (frames_cfg / frames_total)
-        line = {"impl": "reference", "metric": "overlap_steps_per_sec", "value": value, "unit": "steps/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+        value = res["value"]        # latent-px/s of the CPU path does not depend on how many frames one step holds
+        steps_per_sec = res["steps_per_sec"] * (frames_cfg / frames_total)
+        line = {"impl": "reference", "metric": "overlap_latent_px_per_sec", "value": value, "unit": "latent-px/s",
+                "overlap_steps_per_sec": steps_per_sec,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / steps_per_sec,
                 "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{wl}: {frames_total} frames of {H}x{H}x4 int32 ids -> {h}x{h}x4 latents, "
                                        f"ratio {RATIO}; reference CPU torch path (keying cached per id batch as the reference does)"},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "e2e": {"value": value, "unit": "latent-px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         line["cpu_baseline"]["value"] = value
         print(json.dumps(line), flush=True)

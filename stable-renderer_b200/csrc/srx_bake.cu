@@ -60,8 +60,11 @@ __global__ void __launch_bounds__(256) k_bake_claim(const IdT *__restrict__ ids,
         if (!bake_texel(ids, masks, i, g, false, &tex, status)) continue;
         if (g.first_mode && writtens[tex]) continue;
         const long long f = i / hw, pix = i - f * hw;
-        const long long order = (g.first_mode ? (g.frames_total - 1 - f) : f) * hw + pix;
-        atomicMax(owner + tex, (unsigned int)(order + 1));
+        const unsigned int order1 = (unsigned int)((g.first_mode ? (g.frames_total - 1 - f) : f) * hw + pix + 1);
+        // the owner word only grows: skip the atomic when a later pixel already claimed the texel (removes almost all
+        // traffic to hot texels such as (0,0), which every background pixel addresses when no mask is given)
+        if (__ldcg(owner + tex) >= order1) continue;
+        atomicMax(owner + tex, order1);
     }
 }
 
