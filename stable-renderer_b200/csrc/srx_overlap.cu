@@ -19,6 +19,7 @@
 #include "srx_common.cuh"
 #include <cooperative_groups.h>
 #include <new>
+#include <stdlib.h>
 #include <vector>
 
 namespace cg = cooperative_groups;
@@ -26,6 +27,8 @@ namespace cg = cooperative_groups;
 // =================================================================================================================
 // plan
 // =================================================================================================================
+#define SRX_MAX_PEERS 8
+
 struct srx_plan {
     srx_plan_desc d;
     bool fast_r8 = false;
@@ -40,6 +43,10 @@ struct srx_plan {
             status_off = 0, total_bytes = 0;
     int elem = 4;
     int cluster = 1;
+    // frame-sharded peer mode (srx_plan_bind_peers): double-buffered accumulators + signal pads inside the workspace
+    int64_t accum_stride = 0, pads_off = 0, ctrl_off = 0;
+    int world = 1, rank = 0;
+    char *peers[SRX_MAX_PEERS] = {nullptr};
 };
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -48,9 +55,16 @@ static void plan_layout(srx_plan *p) {
     const srx_plan_desc &d = p->d;
     p->elem = d.accum_mode == SRX_ACCUM_DETERMINISTIC ? 8 : 4;
     int64_t off = 0;
+    // [accumulator A0][accumulator A1][signal pads][control words] come first: their offsets depend only on the key
+    // capacity and channel count, so they are identical on every rank of a frame-sharded run
     p->accum_off = off;
     p->accum_bytes = p->kcap * (d.channels + 1) * p->elem;
-    off = align_up(off + p->accum_bytes, 256);
+    p->accum_stride = align_up(p->accum_bytes, 256);
+    off = p->accum_off + 2 * p->accum_stride;
+    p->pads_off = off;
+    off += 256;
+    p->ctrl_off = off;   // [0] step counter, [1] finished-CTA ticket
+    off += 256;
     p->winner_off = off;
     p->winner_bytes = (int64_t)d.batch * d.lat_h * d.lat_w * 4;
     off = align_up(off + p->winner_bytes, 256);
@@ -135,7 +149,7 @@ template <typename IdT, typename XT, bool DET, bool FROM_SLOTS, bool WRITE_SLOTS
 __global__ void __launch_bounds__(256, 3)
 k_accum_r8(const IdT *__restrict__ ids, int *__restrict__ slotmap, const XT *__restrict__ x,
            const int *__restrict__ fmap, void *__restrict__ accum, int *__restrict__ winner, int *__restrict__ status,
-           int H, int W, int h, int w, long long kcap, int nrows, int chunks_per_row) {
+           int H, int W, int h, int w, long long kcap, int nrows, int chunks_per_row, int dbg) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = lane >> 2, pr = lane & 3;
@@ -233,7 +247,7 @@ k_accum_r8(const IdT *__restrict__ ids, int *__restrict__ slotmap, const XT *__r
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int k = k_red[j];
-                if (k < 0) continue;
+                if (k < 0 || (dbg & 1)) continue;
                 if (DET) {
                     const long long q = (long long)m_red[j];
                     red_add_s64(acc_q + (long long)k * 4 + 0, q * to_fix(xv[u][0]));
@@ -627,7 +641,7 @@ extern "C" int srx_plan_bind_workspace(srx_plan *p, void *ws, int64_t bytes, voi
     p->ws = reinterpret_cast<char *>(ws);
     p->ws_bytes = bytes;
     // accumulator starts clean; latent frames that no id frame maps to keep winner = -1 forever
-    SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->accum_off, 0, p->accum_bytes, st));
+    SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->accum_off, 0, (size_t)(2 * p->accum_stride + 512), st));   // A0, A1, pads, ctrl
     SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->winner_off, 0xFF, p->winner_bytes, st));
     SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->status_off, 0, 256, st));
     return SRX_OK;
@@ -656,6 +670,16 @@ extern "C" int srx_plan_check(srx_plan *p, void *stream) {
 // -----------------------------------------------------------------------------------------------------------------
 // launches
 // -----------------------------------------------------------------------------------------------------------------
+// SRX_K1_DEBUG bit 0: skip the reductions (isolates the streaming + keying cost in experiments; results are wrong)
+static int k1_debug_flags() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SRX_K1_DEBUG");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 template <typename IdT, typename XT, bool DET>
 static int launch_accum(srx_plan *p, const srx_step_args *a, cudaStream_t st) {
     const srx_plan_desc &d = p->d;
@@ -670,7 +694,7 @@ static int launch_accum(srx_plan *p, const srx_step_args *a, cudaStream_t st) {
         auto kern = k_accum_r8<IdT, XT, DET, false, false>;
         const int grid = grid_for((const void *)kern, 256, 0, (long long)nrows * chunks);
         kern<<<grid, 256, 0, st>>>(ids, nullptr, x, p->fmap, accum, winner, status, d.height, d.width, d.lat_h, d.lat_w,
-                                   p->kcap, nrows, chunks);
+                                   p->kcap, nrows, chunks, k1_debug_flags());
     } else {
         const long long npx = (long long)d.frames * d.height * d.width;
         const long long ncell_lat = (long long)d.batch * d.lat_h * d.lat_w;
