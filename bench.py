@@ -193,12 +193,15 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
     ids_rot = [ids0] + [torch.roll(ids0, shifts=r, dims=0).contiguous() for r in range(1, n_rot)]
     x = synthetic.make_latents(F_global, 4, h, h, seed=0, dtype=dtype)[f0:f0 + F].contiguous().to(dev)
     x_init = x.clone()
-    plan = OverlapPlan(None, x.shape, id_shape=ids0.shape, id_dtype=ids0.dtype, key_capacity=key_capacity, device=dev)
+    plan = OverlapPlan(None, x.shape, id_shape=ids0.shape, id_dtype=ids0.dtype, key_capacity=key_capacity, device=dev,
+                       process_group=dist.group.WORLD if world > 1 else None, exchange=args.exchange,
+                       split_kernels=args.split_kernels)
     acc = plan.accumulator
+    peer = plan.exchange == "peer"
 
     def one_step(r: int):
-        if world == 1:
-            plan.step(x, RATIO, ids=ids_rot[r])
+        if world == 1 or peer:
+            plan.step(x, RATIO, ids=ids_rot[r])      # one persistent kernel (exchange over NVLink inside it when sharded)
         else:
             plan.reduce(x, ids=ids_rot[r])
             dist.all_reduce(acc, op=dist.ReduceOp.SUM)
@@ -253,23 +256,34 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
     plan.check()
     assert torch.isfinite(x.float()).all(), "latents became non-finite"
 
-    # ---- dominant kernel alone: the id-streaming accumulate pass, per-launch CUDA events --------------------------
-    k1_times = []
+    # ---- dominant kernel alone, per-launch CUDA events (eager launches on the current stream) ----------------------
     n_k1 = min(K, 200)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k1)]
+    elem = x.element_size()
+    step_bytes = 16 * F * H * H + 2 * F * 4 * h * h * elem           # SURVEY.md §8d streaming-regime figure, per GPU
+    fused_kernel = plan.fused and (world == 1 or peer)
+    if fused_kernel:
+        # the whole step is one kernel: ids streamed once, latents read + written once
+        k1_name = "k_overlap_fused (persistent step: id streaming, key reduce, " + \
+                  ("NVLink peer exchange, " if peer else "") + "gather/blend, AdaIN)"
+        k1_bytes = step_bytes
+        k1_call = lambda i: plan.step(x, RATIO, ids=ids_rot[i % n_rot])   # noqa: E731
+    else:
+        k1_name = "k_accum_r8 (id-streaming key/segment-reduce pass)"
+        k1_bytes = 16 * F * H * H + F * 4 * h * h * elem             # ids streamed once + latents read once
+        k1_call = lambda i: plan.reduce(x, ids=ids_rot[i % n_rot])    # noqa: E731
+    x.copy_(x_init)
+    barrier(world)
     for i in range(3):
-        plan.reduce(x, ids=ids_rot[i % n_rot])
+        k1_call(i)
     for i, (a, b) in enumerate(evs):
         a.record()
-        plan.reduce(x, ids=ids_rot[i % n_rot])
+        k1_call(i)
         b.record()
     torch.cuda.synchronize()
-    k1_times = [a.elapsed_time(b) for a, b in evs]
-    k1_ms = statistics.mean(k1_times)
-    acc.zero_()
-    elem = x.element_size()
-    k1_bytes = 16 * F * H * H + F * 4 * h * h * elem                 # ids streamed once + latents read once
-    step_bytes = 16 * F * H * H + 2 * F * 4 * h * h * elem           # SURVEY.md §8d streaming-regime figure, per GPU
+    k1_ms = max_over_ranks(statistics.mean([a.elapsed_time(b) for a, b in evs]), world)
+    if not fused_kernel:
+        acc.zero_()
     peak, peak_src = measured_hbm_peak()
     k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
 
@@ -294,7 +308,8 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
     ed.id_maps, ed.correspond_maps = idm, {(1, 0): _MapSize()}
     ctx = _Ctx()
     ctx.noise, ctx.timestep = x_dev, 900
-    oc = OverlapCorresponder(step_finished_inject_ratio=RATIO, process_group=True if world > 1 else None)
+    oc = OverlapCorresponder(step_finished_inject_ratio=RATIO, process_group=True if world > 1 else None,
+                             exchange=args.exchange)
     n_e2e = max(10, min(K, 200))
 
     def e2e_step(i: int):
@@ -328,8 +343,11 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
                    "frames_per_gpu": F, "frames_total": F_global, "key_capacity": key_capacity,
                    "launch": launch_mode, "fast_path": bool(plan.fast_path),
                    "l2": f"{n_rot} id buffers of {id_bytes >> 20} MiB rotate, so no step finds its ids in the 126 MB L2",
-                   "parallelism": f"frames sharded over {world} GPU(s), NCCL all-reduce of the key accumulator "
-                                  f"({acc.numel() * 4 >> 10} KiB)" if world > 1 else "single GPU"},
+                   "kernels": "one persistent kernel per step" if fused_kernel else "split reduce / gather kernels",
+                   "parallelism": (f"frames sharded over {world} GPU(s), key accumulator ({acc.numel() * 4 >> 10} KiB) "
+                                   + ("exchanged inside the step kernel over NVLink peer memory (reduce-scatter + all-gather)"
+                                      if peer else "summed with one NCCL all-reduce between the reduce and gather kernels"))
+                   if world > 1 else "single GPU"},
         "overlap_steps_per_sec": 1e3 / ms_step,
         "id_px_per_sec": F_global * H * H * 1e3 / ms_step,
         "clocks": clocks,
@@ -337,8 +355,8 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
                 "h2d_bytes_per_step": id_bytes + x.numel() * elem, "d2h_bytes_per_step": x.numel() * elem,
                 "ms_per_step": e2e_ms, "steps_per_sec": 1e3 / e2e_ms, "steps": n_e2e,
                 "api": "OverlapCorresponder.step_finished(engine_data, sampling_context)"},
-        "gpu_launches": 2 * K if plan.fast_path else 3 * K,
-        "roofline": {"bound": "hbm", "kernel": "k_accum_r8 (id-streaming key/segment-reduce pass)",
+        "gpu_launches": K if fused_kernel else (2 * K if plan.fast_path else 3 * K),
+        "roofline": {"bound": "hbm", "kernel": k1_name,
                      "achieved": k1_gbs, "peak": peak, "unit": "GB/s", "frac": k1_gbs / peak,
                      "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
                      "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
@@ -437,6 +455,9 @@ def main():
     ap.add_argument("--workload", choices=list(WORKLOADS) + ["bake"], default="cfg2")
     ap.add_argument("--bake-weight", default="view_normal_depth", choices=["none", "uniform", "view_normal", "view_normal_depth"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", choices=["auto", "peer", "nccl"], default="auto",
+                    help="multi-GPU accumulator exchange: inside the step kernel over NVLink peer memory, or NCCL all-reduce")
+    ap.add_argument("--split-kernels", action="store_true", help="run the split reduce / gather kernels instead of the persistent one")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

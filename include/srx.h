@@ -60,7 +60,9 @@ typedef enum srx_strategy { /* legacy_codes/stable_rendering_algo/overlap/algori
 
 typedef enum srx_accum_mode {
     SRX_ACCUM_FAST = 0,         /* float32 vector atomics (order not fixed; within 1e-5 of the reference) */
-    SRX_ACCUM_DETERMINISTIC = 1 /* Q31.32 fixed-point int64 atomics: order independent, bit reproducible */
+    SRX_ACCUM_DETERMINISTIC = 1,/* Q31.32 fixed-point int64 atomics: order independent, bit reproducible */
+    SRX_ACCUM_FAST_SPLIT = 2    /* as FAST, but srx_overlap_step always runs the split reduce + gather kernels instead of
+                                   the single persistent kernel (profiling / cross-checking) */
 } srx_accum_mode;
 
 int srx_version(void);
@@ -98,6 +100,7 @@ typedef struct srx_plan_info {
     int64_t accum_bytes;     /* ... i.e. the buffer a multi-GPU caller all-reduces between reduce and gather */
     int accum_dtype;         /* SRX_F32 (fast) — int64 in deterministic mode is reported as -64 */
     int fast_path;           /* 1 when the 8x8-pixels-per-cell warp kernel applies */
+    int fused;               /* 1 when srx_overlap_step runs as the single persistent kernel (and peer mode is available) */
 } srx_plan_info;
 
 /* Builds the plan for one batch of id buffers.  `ids_dev` may be NULL when key_capacity > 0 (ids are then given to
@@ -106,6 +109,15 @@ typedef struct srx_plan_info {
 int srx_plan_create(srx_plan **out, const srx_plan_desc *desc, const void *ids_dev, void *stream);
 int srx_plan_get_info(const srx_plan *plan, srx_plan_info *info);
 int srx_plan_bind_workspace(srx_plan *plan, void *workspace_dev, int64_t bytes, void *stream);
+/* Frame-sharded peer mode: `peer_workspaces[i]` is rank i's bound workspace as mapped into this
+ * process (CUDA IPC / symmetric memory; entry `rank` is ignored).  All ranks bind workspaces of identical layout
+ * (same key capacity and channels) on GPUs with the same SM count.  Afterwards srx_overlap_step reduces this rank's
+ * frames, exchanges the key accumulator with the peers over NVLink inside the same kernel, and gathers this rank's
+ * frames; every rank must call it the same number of times.  world = 1 unbinds. */
+int srx_plan_bind_peers(srx_plan *plan, int rank, int world, void *const *peer_workspaces);
+/* CTAs of the persistent step kernel (default 0 = one per SM).  Every rank of a peer group must use the same value;
+ * smaller grids let several ranks' kernels share one GPU (single-GPU emulation of a frame-sharded run in the tests). */
+int srx_plan_set_grid(srx_plan *plan, int ctas);
 int srx_plan_destroy(srx_plan *plan);
 /* Lazily reported device-side failures of earlier launches (key out of the slot table, cell out of range).
  * Syncs the stream. */

@@ -15,7 +15,7 @@ SRX_OK, SRX_ERR_INVALID, SRX_ERR_INDEX, SRX_ERR_CUDA, SRX_ERR_UNSUPPORTED, SRX_E
 SRX_F32, SRX_F16, SRX_BF16, SRX_I32, SRX_I16, SRX_U8 = 0, 1, 2, 10, 11, 20
 SRX_KEY_VERTEX, SRX_KEY_TUPLE = 0, 1
 SRX_STRATEGY = {"average": 0, "frame_distance": 1, "pixel_distance": 2, "perpendicular_view_normal": 3}
-SRX_ACCUM_FAST, SRX_ACCUM_DETERMINISTIC = 0, 1
+SRX_ACCUM_FAST, SRX_ACCUM_DETERMINISTIC, SRX_ACCUM_FAST_SPLIT = 0, 1, 2
 SRX_BAKE_MODE = {"replace": 0, "replace_avg": 1, "first": 2, "first_avg": 3}
 SRX_BAKE_WEIGHT = {None: 0, "none": 0, "uniform": 1, "view_normal": 2, "view_normal_depth": 3}
 
@@ -38,7 +38,7 @@ class srx_plan_desc(C.Structure):
 class srx_plan_info(C.Structure):
     _fields_ = [("n_valid", C.c_int64), ("key_min", C.c_int64), ("key_max", C.c_int64), ("key_capacity", C.c_int64),
                 ("workspace_bytes", C.c_int64), ("accum_offset", C.c_int64), ("accum_bytes", C.c_int64),
-                ("accum_dtype", C.c_int), ("fast_path", C.c_int)]
+                ("accum_dtype", C.c_int), ("fast_path", C.c_int), ("fused", C.c_int)]
 
 
 class srx_step_args(C.Structure):
@@ -74,6 +74,8 @@ _PROTOTYPES = {
     "srx_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(srx_plan_desc), C.c_void_p, C.c_void_p]),
     "srx_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(srx_plan_info)]),
     "srx_plan_bind_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "srx_plan_bind_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "srx_plan_set_grid": (C.c_int, [C.c_void_p, C.c_int]),
     "srx_plan_destroy": (C.c_int, [C.c_void_p]),
     "srx_plan_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "srx_vertex_screen_info": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32),

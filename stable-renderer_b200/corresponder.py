@@ -95,9 +95,11 @@ class OverlapCorresponder:
     deterministic: bool = attrib(default=False, kw_only=True)
     adain: bool = attrib(default=True, kw_only=True)
     process_group: Any = attrib(default=None, kw_only=True)
+    exchange: str = attrib(default="auto", kw_only=True)
     '''frame-sharded multi-GPU runs (SURVEY.md §8e): when set, every rank reduces its own frames into the key-indexed
-    accumulator, the accumulators are summed with one NCCL all-reduce over this torch.distributed group, then each
-    rank gathers its own frames.  Pass `torch.distributed.group.WORLD` (or True) for the default group.'''
+    accumulator, the accumulators are summed across ranks, then each rank gathers its own frames.  Pass
+    `torch.distributed.group.WORLD` (or True) for the default group.  `exchange`: "peer" = the sum runs inside the step
+    kernel over NVLink peer memory, "nccl" = one NCCL all-reduce between two kernels, "auto" = peer when available.'''
 
     def prepare(self, engine_data: "EngineData"):
         pass
@@ -135,8 +137,13 @@ class OverlapCorresponder:
                 kmax = ids_dev[..., 3].max().to(torch.int64).reshape(1)
                 dist.all_reduce(kmax, op=dist.ReduceOp.MAX, group=None if self.process_group is True else self.process_group)
                 cap = int(kmax.item()) + 1
+            group = None
+            if self.process_group is not None:
+                import torch.distributed as dist
+                group = dist.group.WORLD if self.process_group is True else self.process_group
             plan = OverlapPlan(ids_dev, x.shape, frame_indices=id_map.frame_indices,
-                               key_capacity=cap, deterministic=self.deterministic)
+                               key_capacity=cap, deterministic=self.deterministic, process_group=group,
+                               exchange=self.exchange)
             id_map._plans[key] = plan
         return plan
 
@@ -150,8 +157,8 @@ class OverlapCorresponder:
             raise _lib.SrxUnavailable("sampling_context.noise must be a CUDA tensor (there is no CPU path)")
         x = noise if noise.is_contiguous() else noise.contiguous()
         plan = self._plan(engine_data, id_map, x)
-        if self.process_group is None:
-            plan.step(x, self.step_finished_inject_ratio, adain=self.adain)
+        if self.process_group is None or plan.exchange == "peer":
+            plan.step(x, self.step_finished_inject_ratio, adain=self.adain)   # one kernel, exchange included
         else:
             import torch.distributed as dist
             group = None if self.process_group is True else self.process_group

@@ -16,7 +16,7 @@
 //   [NCCL all-reduce of the accumulator when frames are sharded over GPUs]
 //   K2  finalize   : one thread-block cluster per latent frame: gather the winner key's mean, blend, per-(frame,
 //                    channel) statistics reduced over distributed shared memory, AdaIN, in-place write-back.
-#include "srx_common.cuh"
+#include "srx_plan.cuh"
 #include <cooperative_groups.h>
 #include <new>
 #include <stdlib.h>
@@ -27,55 +27,6 @@ namespace cg = cooperative_groups;
 // =================================================================================================================
 // plan
 // =================================================================================================================
-#define SRX_MAX_PEERS 8
-
-struct srx_plan {
-    srx_plan_desc d;
-    bool fast_r8 = false;
-    int64_t kcap = 0, n_valid = -1, key_min = 0, key_max = -1;
-    // device tables (one allocation)
-    int *tables = nullptr;
-    int *colcell = nullptr, *rowcell = nullptr, *fmap = nullptr;
-    // workspace (caller owned)
-    char *ws = nullptr;
-    int64_t ws_bytes = 0;
-    int64_t accum_off = 0, accum_bytes = 0, winner_off = 0, winner_bytes = 0, winner64_off = 0, winner64_bytes = 0,
-            status_off = 0, total_bytes = 0;
-    int elem = 4;
-    int cluster = 1;
-    // frame-sharded peer mode (srx_plan_bind_peers): double-buffered accumulators + signal pads inside the workspace
-    int64_t accum_stride = 0, pads_off = 0, ctrl_off = 0;
-    int world = 1, rank = 0;
-    char *peers[SRX_MAX_PEERS] = {nullptr};
-};
-
-static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
-
-static void plan_layout(srx_plan *p) {
-    const srx_plan_desc &d = p->d;
-    p->elem = d.accum_mode == SRX_ACCUM_DETERMINISTIC ? 8 : 4;
-    int64_t off = 0;
-    // [accumulator A0][accumulator A1][signal pads][control words] come first: their offsets depend only on the key
-    // capacity and channel count, so they are identical on every rank of a frame-sharded run
-    p->accum_off = off;
-    p->accum_bytes = p->kcap * (d.channels + 1) * p->elem;
-    p->accum_stride = align_up(p->accum_bytes, 256);
-    off = p->accum_off + 2 * p->accum_stride;
-    p->pads_off = off;
-    off += 256;
-    p->ctrl_off = off;   // [0] step counter, [1] finished-CTA ticket
-    off += 256;
-    p->winner_off = off;
-    p->winner_bytes = (int64_t)d.batch * d.lat_h * d.lat_w * 4;
-    off = align_up(off + p->winner_bytes, 256);
-    p->winner64_off = off;
-    p->winner64_bytes = p->fast_r8 ? 0 : (int64_t)d.batch * d.lat_h * d.lat_w * 8;
-    off = align_up(off + p->winner64_bytes, 256);
-    p->status_off = off;
-    off += 256;
-    p->total_bytes = off;
-}
-
 // cell coordinate of a pixel coordinate, in the reference's float32 arithmetic:
 // trunc(fl32(fl32(p) / fl32(divisor)) * fl32(cells))   (corrmap.py:239,249 ; corresponder.py:312-313)
 static int host_cell(int p, int divisor, int cells) {
@@ -553,7 +504,8 @@ extern "C" int srx_plan_create(srx_plan **out, const srx_plan_desc *desc, const 
                 SRX_ERR_INVALID, "non-positive dimension");
     SRX_REQUIRE(d.channels <= 64, SRX_ERR_UNSUPPORTED, "more than 64 latent channels");
     SRX_REQUIRE(d.key_mode == SRX_KEY_VERTEX, SRX_ERR_UNSUPPORTED, "srx_plan_create handles SRX_KEY_VERTEX; tuple keys go through srx_legacy_*");
-    SRX_REQUIRE(d.accum_mode == SRX_ACCUM_FAST || d.accum_mode == SRX_ACCUM_DETERMINISTIC, SRX_ERR_INVALID, "bad accum mode");
+    SRX_REQUIRE(d.accum_mode == SRX_ACCUM_FAST || d.accum_mode == SRX_ACCUM_DETERMINISTIC || d.accum_mode == SRX_ACCUM_FAST_SPLIT,
+                SRX_ERR_INVALID, "bad accum mode");
     SRX_REQUIRE(d.key_capacity > 0 || ids_dev, SRX_ERR_INVALID, "ids are required when key_capacity is 0 (scan)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
@@ -561,6 +513,8 @@ extern "C" int srx_plan_create(srx_plan **out, const srx_plan_desc *desc, const 
     SRX_REQUIRE(p, SRX_ERR_INVALID, "out of host memory");
     p->d = d;
     p->d.frame_map = nullptr;
+    const bool allow_fused = d.accum_mode == SRX_ACCUM_FAST;
+    if (d.accum_mode == SRX_ACCUM_FAST_SPLIT) p->d.accum_mode = SRX_ACCUM_FAST;
 
     // host tables in the reference's float32 arithmetic
     std::vector<int> tab((size_t)d.width + d.height + d.frames);
@@ -612,6 +566,7 @@ extern "C" int srx_plan_create(srx_plan **out, const srx_plan_desc *desc, const 
         return srx_set_error(SRX_ERR_KEY_RANGE, "key capacity %lld exceeds the dense slot table limit 2^25", (long long)k);
     }
     p->kcap = align_up(p->kcap, 64);
+    p->fused = allow_fused && srx_fused_applicable(p);
     plan_layout(p);
     const int n = d.lat_h * d.lat_w;
     p->cluster = n >= 16384 ? 8 : (n >= 4096 ? 4 : (n >= 1024 ? 2 : 1));
@@ -630,6 +585,7 @@ extern "C" int srx_plan_get_info(const srx_plan *p, srx_plan_info *info) {
     info->accum_bytes = p->accum_bytes;
     info->accum_dtype = p->d.accum_mode == SRX_ACCUM_DETERMINISTIC ? -64 : SRX_F32;
     info->fast_path = p->fast_r8 ? 1 : 0;
+    info->fused = p->fused ? 1 : 0;
     return SRX_OK;
 }
 
@@ -641,7 +597,8 @@ extern "C" int srx_plan_bind_workspace(srx_plan *p, void *ws, int64_t bytes, voi
     p->ws = reinterpret_cast<char *>(ws);
     p->ws_bytes = bytes;
     // accumulator starts clean; latent frames that no id frame maps to keep winner = -1 forever
-    SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->accum_off, 0, (size_t)(2 * p->accum_stride + 512), st));   // A0, A1, pads, ctrl
+    SRX_CUDA_CHECK(cudaMemsetAsync(p->ws, 0, (size_t)(3 * p->accum_stride + 512), st));   // A0, A1, A2, pads, ctrl
+    SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->stats_off, 0, (size_t)p->stats_bytes, st));
     SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->winner_off, 0xFF, p->winner_bytes, st));
     SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->status_off, 0, 256, st));
     return SRX_OK;
@@ -782,6 +739,13 @@ extern "C" int srx_accum_finalize_gather(srx_plan *p, const srx_step_args *a, vo
 }
 
 extern "C" int srx_overlap_step(srx_plan *p, const srx_step_args *a, void *stream) {
+    if (p && a && p->fused) {
+        int rc0 = check_step(p, a);
+        if (rc0) return rc0;
+        SRX_REQUIRE(a->ids_dev, SRX_ERR_INVALID, "pass ids_dev");
+        return srx_launch_fused(p, a, reinterpret_cast<cudaStream_t>(stream));
+    }
+    SRX_REQUIRE(p && p->world == 1, SRX_ERR_UNSUPPORTED, "peer mode is only available with the persistent step kernel");
     int rc = srx_accum_reduce(p, a, stream);
     if (rc) return rc;
     return srx_accum_finalize_gather(p, a, stream);

@@ -17,7 +17,12 @@ class OverlapPlan:
     def __init__(self, ids: Optional[torch.Tensor], latent_shape: Sequence[int], *,
                  frame_indices: Optional[Sequence[int]] = None, id_shape: Optional[Sequence[int]] = None,
                  id_dtype: Optional[torch.dtype] = None, key_capacity: int = 0, deterministic: bool = False,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, process_group=None, exchange: str = "auto",
+                 split_kernels: bool = False):
+        """process_group: frame-sharded run — every rank holds its own frames and the same key
+        capacity.  exchange: "peer" = the accumulator exchange runs inside the step kernel over NVLink peer memory
+        (workspace allocated as torch symmetric memory), "nccl" = reduce / all_reduce / gather as three launches,
+        "auto" = peer when it can be set up, else nccl."""
         lib = _lib.load()
         if ids is not None:
             if not ids.is_cuda:
@@ -42,7 +47,8 @@ class OverlapPlan:
         desc.batch, desc.channels, desc.lat_h, desc.lat_w = B, Cc, h, w
         desc.key_mode = _lib.SRX_KEY_VERTEX
         desc.merge_len = 0
-        desc.accum_mode = _lib.SRX_ACCUM_DETERMINISTIC if deterministic else _lib.SRX_ACCUM_FAST
+        desc.accum_mode = (_lib.SRX_ACCUM_DETERMINISTIC if deterministic else
+                           _lib.SRX_ACCUM_FAST_SPLIT if split_kernels else _lib.SRX_ACCUM_FAST)
         desc.key_capacity = int(key_capacity)
         fm = None
         if frame_indices is not None:
@@ -58,11 +64,73 @@ class OverlapPlan:
             info = _lib.srx_plan_info()
             _lib.check(lib.srx_plan_get_info(self._handle, C.byref(info)))
             self.info = info
-            self.workspace = torch.empty(int(info.workspace_bytes), dtype=torch.uint8, device=self.device)
-            _lib.check(lib.srx_plan_bind_workspace(self._handle, self.workspace.data_ptr(), int(info.workspace_bytes), stream))
+            self.fused = bool(info.fused)
+            self.group = process_group
+            self.world = 1
+            self.exchange = "none"
+            self._symm = None
+            nbytes = int(info.workspace_bytes)
+            if process_group is not None:
+                import torch.distributed as dist
+                self.world = dist.get_world_size(process_group)
+                self.exchange = "nccl"
+            want_peer = self.world > 1 and exchange in ("auto", "peer")
+            if exchange == "peer" and self.world > 1 and not self.fused:
+                raise _lib.SrxError("exchange='peer' needs the persistent step kernel (8x8 pixels per cell, 4 channels, "
+                                    "non-deterministic accumulators)")
+            self.workspace = None
+            if want_peer and self.fused:
+                self.workspace = self._alloc_symmetric(nbytes, exchange == "peer")
+            if self.workspace is None:
+                self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.check(lib.srx_plan_bind_workspace(self._handle, self.workspace.data_ptr(), nbytes, stream))
+            if self._symm is not None:
+                self._bind_peers(lib)
         self.key_capacity = int(info.key_capacity)
         self.n_valid = int(info.n_valid)
         self.fast_path = bool(info.fast_path)
+
+    # -- frame-sharded peer mode -----------------------------------------------------------------------------
+    def _alloc_symmetric(self, nbytes: int, required: bool) -> Optional[torch.Tensor]:
+        """Workspace as torch symmetric memory (plumbing only: it hands every rank the peers' device pointers).
+        All ranks of the group must succeed or fail together, so the outcome is agreed with one all_reduce."""
+        import torch.distributed as dist
+        ws, err = None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            ws = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._symm = symm_mem.rendezvous(ws, group=self.group)
+        except Exception as e:  # noqa: BLE001 - any failure means "no peer mapping on this box"
+            ws, err, self._symm = None, e, None
+        ok = torch.tensor([1 if ws is not None else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self._symm = None
+            if required:
+                raise _lib.SrxError(f"peer exchange unavailable: symmetric memory rendezvous failed ({err})")
+            return None
+        return ws
+
+    def _bind_peers(self, lib) -> None:
+        import torch.distributed as dist
+        rank = dist.get_rank(self.group)
+        ptrs = [int(v) for v in self._symm.buffer_ptrs]
+        assert len(ptrs) == self.world
+        arr = (C.c_void_p * self.world)(*ptrs)
+        torch.cuda.synchronize(self.device)          # the clears issued by bind_workspace have landed ...
+        dist.barrier(group=self.group)               # ... on every rank before anyone signals a peer
+        _lib.check(lib.srx_plan_bind_peers(self._handle, rank, self.world, arr))
+        self.exchange = "peer"
+
+    def bind_peers(self, rank: int, peer_workspaces: Sequence[int]) -> None:
+        """Low-level peer binding from raw workspace device pointers (tests emulate two ranks on one GPU with it)."""
+        world = len(peer_workspaces)
+        arr = (C.c_void_p * world)(*[int(v) for v in peer_workspaces])
+        _lib.check(_lib.load().srx_plan_bind_peers(self._handle, int(rank), world, arr))
+        self.world, self.exchange = world, ("peer" if world > 1 else "none")
+
+    def set_grid(self, ctas: int) -> None:
+        _lib.check(_lib.load().srx_plan_set_grid(self._handle, int(ctas)))
 
     # -- accumulator view for the multi-GPU exchange (SURVEY.md §8e) ---------------------------------------
     @property

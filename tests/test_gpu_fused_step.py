@@ -1,0 +1,151 @@
+"""-m gpu tests of the persistent single-kernel overlap step (csrc/srx_fused.cu): against the numpy oracle, against the
+split reduce + gather kernels, over consecutive steps (double-buffered accumulators / device step counter), on ragged
+rows, replayed from a CUDA graph, and its in-kernel peer exchange emulated with two ranks on one GPU (plus a real
+2-GPU run when two devices are visible)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import srx_oracle as O
+from helpers import assert_close, t2n
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 3e-6
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _inputs(F, H, W, tex, seed, id_dtype=torch.int32, frac_2048=0.05, n_obj=1):
+    from stable_renderer_b200 import synthetic
+    ids = synthetic.make_ids(F, H, W, tex_h=tex, tex_w=tex, frac_2048=frac_2048, seed=seed, dtype=id_dtype, n_obj=n_obj)
+    x = synthetic.make_latents(F, 4, H // 8, W // 8, seed=seed + 1)
+    return ids, x
+
+
+@pytest.mark.parametrize("shape", [(4, 256, 256), (3, 320, 320), (1, 576, 576)])
+@pytest.mark.parametrize("adain", [True, False])
+def test_fused_step_matches_oracle(shape, adain):
+    """w = 32 (one full chunk per row), w = 40 (a 32-cell and an 8-cell chunk) and w = 72 (two full chunks + 8 cells).
+    Only square id buffers are valid: the reference divides x by the HEIGHT (corrmap.py:239)."""
+    from stable_renderer_b200.plan import OverlapPlan
+    F, H, W = shape
+    ids, x0 = _inputs(F, H, W, 128, seed=11)
+    want, parts = O.overlap_step(x0.numpy(), ids.numpy(), None, ratio=0.5, accumulate="f64", return_parts=True)
+    if not adain:
+        want = parts["blended"]          # adain=False writes the blended latents (before AdaIN)
+    x = x0.cuda()
+    plan = OverlapPlan(ids.cuda(), x.shape, key_capacity=128 * 128)
+    assert plan.fused and plan.fast_path
+    plan.step(x, 0.5, adain=adain)
+    plan.check()
+    assert_close(t2n(x), want, RTOL, ATOL, f"fused {shape} adain={adain}")
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, (1e-5, 3e-6)), (torch.float16, (1e-2, 1e-2)), (torch.bfloat16, (1e-2, 2e-2))])
+@pytest.mark.parametrize("id_dtype", [torch.int32, torch.int16])
+def test_fused_equals_split_kernels(dtype, tol, id_dtype):
+    from stable_renderer_b200.plan import OverlapPlan
+    tex = 128 if id_dtype == torch.int16 else 256     # int16 vertex ids must stay below 32768
+    ids, x0 = _inputs(6, 256, 256, tex, seed=5, id_dtype=id_dtype)
+    ids = ids.cuda()
+    a = x0.to(dtype).cuda()
+    b = a.clone()
+    pf = OverlapPlan(ids, a.shape, key_capacity=tex * tex)
+    ps = OverlapPlan(ids, b.shape, key_capacity=tex * tex, split_kernels=True)
+    assert pf.fused and not ps.fused
+    pf.step(a, 0.3)
+    ps.step(b, 0.3)
+    torch.cuda.synchronize()
+    assert_close(t2n(a), t2n(b), tol[0], tol[1], f"fused vs split {dtype} {id_dtype}")
+
+
+def test_fused_consecutive_steps_and_graph_replay():
+    """Five steps on one plan (accumulator parity, statistics double buffer, barrier targets from the device step
+    counter) eagerly and replayed from a CUDA graph; both must track the oracle applied five times."""
+    from stable_renderer_b200.plan import OverlapPlan
+    ids, x0 = _inputs(4, 256, 256, 128, seed=21)
+    want = x0.numpy()
+    for _ in range(5):
+        want = O.overlap_step(want, ids.numpy(), None, ratio=0.5, accumulate="f64")
+    ids_d = ids.cuda()
+    x = x0.cuda()
+    plan = OverlapPlan(ids_d, x.shape, key_capacity=128 * 128)
+    for _ in range(5):
+        plan.step(x, 0.5)
+    plan.check()
+    assert_close(t2n(x), want, 5e-5, 1e-5, "5 eager steps")
+
+    xg = x0.cuda()
+    plan2 = OverlapPlan(ids_d, xg.shape, key_capacity=128 * 128)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        plan2.step(xg, 0.5)                       # step 1 eagerly (warm-up outside capture)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        plan2.step(xg, 0.5)
+    for _ in range(4):                            # capture does not execute: 4 replays = steps 2..5
+        graph.replay()
+    torch.cuda.synchronize()
+    plan2.check()
+    assert_close(t2n(xg), want, 5e-5, 1e-5, "1 eager + 4 replayed steps")
+
+
+def test_fused_key_out_of_range_is_reported():
+    from stable_renderer_b200 import _lib
+    from stable_renderer_b200.plan import OverlapPlan
+    ids, x0 = _inputs(2, 128, 128, 128, seed=3)
+    x = x0.cuda()
+    plan = OverlapPlan(ids.cuda(), x.shape, key_capacity=1000)     # vertex ids reach 16383
+    assert plan.fused
+    plan.step(x, 0.5)
+    with pytest.raises(_lib.SrxError):
+        plan.check()
+
+
+def test_fused_peer_exchange_two_ranks_on_one_gpu():
+    """The in-kernel accumulator exchange (phase X) with two 'ranks' sharing this GPU: each plan runs on half of the SMs
+    on its own stream, the peers' workspaces are each other's.  Must equal one plan over all frames — for several
+    consecutive steps, since each step's barriers build on the previous step's counters."""
+    from stable_renderer_b200 import _lib
+    from stable_renderer_b200.plan import OverlapPlan
+    sms = _lib.load().srx_device_sm_count()
+    F, H = 8, 256
+    ids, x0 = _inputs(F, H, H, 256, seed=77)
+    ids = ids.cuda()
+    ref = x0.cuda()
+    cap = 256 * 256
+    pref = OverlapPlan(ids, ref.shape, key_capacity=cap)
+    xs = [x0[r * F // 2:(r + 1) * F // 2].contiguous().cuda() for r in range(2)]
+    plans = [OverlapPlan(ids[r * F // 2:(r + 1) * F // 2].contiguous(), xs[r].shape, key_capacity=cap) for r in range(2)]
+    ptrs = [p.workspace.data_ptr() for p in plans]
+    for r, p in enumerate(plans):
+        p.set_grid(sms // 2)
+        p.bind_peers(r, ptrs)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for step in range(3):
+        pref.step(ref, 0.5)
+        torch.cuda.synchronize()
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                plans[r].step(xs[r], 0.5)
+        torch.cuda.synchronize()
+        got = torch.cat(xs, dim=0)
+        assert_close(t2n(got), t2n(ref), 2e-5, 5e-6, f"peer exchange, step {step}")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_fused_peer_exchange_two_gpus():
+    """Real frame-sharded run: 2 processes, symmetric-memory workspaces, exchange inside the step kernel over NVLink."""
+    script = os.path.join(ROOT, "tests", "mp_peer_worker.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", script]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
+    assert "PEER_OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
