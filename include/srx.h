@@ -118,6 +118,13 @@ int srx_plan_bind_peers(srx_plan *plan, int rank, int world, void *const *peer_w
 /* CTAs of the persistent step kernel (default 0 = one per SM).  Every rank of a peer group must use the same value;
  * smaller grids let several ranks' kernels share one GPU (single-GPU emulation of a frame-sharded run in the tests). */
 int srx_plan_set_grid(srx_plan *plan, int ctas);
+/* Profiling aid: SM-clock timestamps of the phases of the last persistent step (first CTA in out16[0..7], last CTA in
+ * out16[8..15]; index meaning in csrc/srx_fused.cu).  Syncs. */
+int srx_plan_read_trace(srx_plan *plan, int64_t *out16, void *stream);
+/* Profiling aid: (earliest CTA start, latest CTA end) of the last 32 persistent steps on the GPU global timer [ns],
+ * out64[2 * (step & 31) + {0,1}], then the first CTA's phase stamps of those steps, out64[64 + 8 * (step & 31) + idx]
+ * (320 values in all).  Syncs. */
+int srx_plan_read_step_ring(srx_plan *plan, uint64_t *out64, void *stream);
 int srx_plan_destroy(srx_plan *plan);
 /* Lazily reported device-side failures of earlier launches (key out of the slot table, cell out of range).
  * Syncs the stream. */

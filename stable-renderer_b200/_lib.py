@@ -76,6 +76,8 @@ _PROTOTYPES = {
     "srx_plan_bind_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "srx_plan_bind_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "srx_plan_set_grid": (C.c_int, [C.c_void_p, C.c_int]),
+    "srx_plan_read_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "srx_plan_read_step_ring": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "srx_plan_destroy": (C.c_int, [C.c_void_p]),
     "srx_plan_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "srx_vertex_screen_info": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32),

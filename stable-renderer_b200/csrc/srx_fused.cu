@@ -29,6 +29,7 @@
 #define FZ_CPW (FZ_CELLS / FZ_CONS)       // cells per consumer warp per stage
 #define FZ_STAGES 6
 #define FZ_SLOT_BITS 25
+#define FZ_BU 2                           // cells per thread per round of the gather phase
 
 enum { FZ_ST_KEY_RANGE = 0 };
 
@@ -56,6 +57,8 @@ struct FzParams {
     const int *fmap;
     char *ws;                 // this rank's workspace
     char *peers[SRX_MAX_PEERS];
+    long long ll_off;         // this rank's total records [ceil(kcap / world)] of 32 B (peer mode)
+    int ll_slice;             // slots per owner slice = ceil(kcap / world)
     long long accum_stride, pads_off, ctrl_off, stats_off;
     int *winner;
     int *status;
@@ -135,16 +138,64 @@ __device__ __forceinline__ void red_release_add(unsigned *p, unsigned v, bool sy
     if (sys) asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
     else asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_add(unsigned *p, unsigned v) {
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire(const unsigned *p, bool sys) {
     unsigned v;
     if (sys) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned *p, bool sys) {
+    unsigned v;
+    if (sys) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ float4 ld_volatile_f4(const float4 *p) {
     float4 v;
     asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
+}
+
+// phase timestamps (SM clock) of the first and the last CTA, kept in the control block: [ctrl + 64 + 64*which][8]
+#define FZ_TRACE(idx)                                                                                              \
+    do {                                                                                                           \
+        if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {                                        \
+            const long long now_ = clock64();                                                                      \
+            reinterpret_cast<long long *>(P.ws + P.ctrl_off + 64 + (blockIdx.x == 0 ? 0 : 64))[idx] = now_;        \
+            if (blockIdx.x == 0) reinterpret_cast<long long *>(P.ws + P.ctrl_off + 1024)[(fz_epoch_ & 31u) * 8 + idx] = now_; \
+        }                                                                                                          \
+    } while (0)
+
+// 32-byte exchange record {sum.xyzw, count, flag, -, -}: written with ONE 256-bit store and read with ONE 256-bit load,
+// so data and flag travel in the same sector and a reader that sees this step's flag also sees this step's data — no
+// fence, no acknowledgement round trip, no separate barrier (same idea as NCCL's LL protocols).  Flags are the step
+// number: records never need clearing.
+struct FzRec { float4 s; float c; unsigned flag; };
+__device__ __forceinline__ void fz_rec_store(char *p, float4 s, float c, unsigned flag) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(__float_as_uint(s.x)), "r"(__float_as_uint(s.y)), "r"(__float_as_uint(s.z)), "r"(__float_as_uint(s.w)),
+                   "r"(__float_as_uint(c)), "r"(flag), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ FzRec fz_rec_load(const char *p) {
+    unsigned a, b, c, d, e, f, g, h;
+    asm volatile("ld.relaxed.sys.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(f), "=r"(g), "=r"(h) : "l"(p) : "memory");
+    FzRec r;
+    r.s = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+    r.c = __uint_as_float(e);
+    r.flag = f;
+    return r;
+}
+__device__ __forceinline__ FzRec fz_rec_wait(const char *p, unsigned flag) {
+    FzRec r = fz_rec_load(p);
+    while (r.flag != flag) {
+        __nanosleep(200);   // thousands of threads wait at once: back off instead of saturating L2 with polls
+        r = fz_rec_load(p);
+    }
+    return r;
 }
 
 // Grid-wide (and, with peers, box-wide) barrier `b`: every CTA adds 1 to counter [b][my rank] on each participant and
@@ -155,22 +206,30 @@ __device__ __forceinline__ void fz_barrier(const FzParams &P, int b, unsigned ta
     const int nsrc = cross ? P.world : 1;
     const bool sys = cross && P.world > 1;
     if (threadIdx.x < nsrc) {
-        if (sys) __threadfence_system();
         const int dst = cross ? (int)threadIdx.x : P.rank;
         unsigned *pad = reinterpret_cast<unsigned *>((cross ? P.peers[dst] : P.ws) + P.pads_off) + b * SRX_MAX_PEERS + P.rank;
-        red_release_add(pad, 1u, sys);
+        // the __threadfence() above made this CTA's writes visible in this GPU's L2, which is also where peers read
+        // them; the arrival itself is a relaxed add (a system-scope release would stall for microseconds)
+        if (sys) red_relaxed_add(pad, 1u);
+        else red_release_add(pad, 1u, false);
         const int src = cross ? (int)threadIdx.x : P.rank;
         const unsigned *mine = reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + b * SRX_MAX_PEERS + src;
-        while ((int)(ld_acquire(mine, sys) - target) < 0) __nanosleep(32);
+        while ((int)(ld_relaxed(mine, sys) - target) < 0) { }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }
 
 // key of one pixel: the dense slot of float32(vertexID) (corresponder.py:331-334, corrmap.py:256-261) or -1 when the
 // pixel is no entry (map_index == 2048 or an all-zero id, corrmap.py:266-275)
+// float32(v) in integer arithmetic: exact below 2^24; in [2^24, 2^25) floats are 2 apart and ties go to the even
+// mantissa, i.e. the multiple of 4; from 2^25 on the value is past any slot table (capacity <= 2^25) whatever it rounds to.
+__device__ __forceinline__ int fz_slot_of(int v) {
+    return ((unsigned)v >> 24) == 1u ? ((v + ((v >> 1) & 1)) & ~1) : v;
+}
 __device__ __forceinline__ int fz_key(int s, int m, int i, int v, unsigned kcap, int *status) {
     const bool valid = (i != SRX_NO_ID_MAP_INDEX) & ((s | m | i | v) != 0);
-    const int slot = __float2int_rz(__int2float_rn(v));
+    const int slot = fz_slot_of(v);
     const bool inr = (unsigned)slot < kcap;
     if (valid & !inr) atomicOr(status + FZ_ST_KEY_RANGE, 1);
     return (valid & inr) ? slot : -1;
@@ -192,6 +251,44 @@ __device__ __forceinline__ double fz_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Exchange, owner side: pull the partial sums of this rank's slots from every peer, add in rank order, keep the totals
+// as flagged records.  U slots per thread and round, all their loads in flight together (one NVLink round trip per round);
+// U * MAXP is bounded by the register budget.
+template <int U, int MAXP>
+__device__ __forceinline__ void fz_pull_slice(const FzParams &P, const float *acc, long long aoff, int slice, unsigned epoch,
+                                              int gtid, int gthreads) {
+    (void)acc;
+    for (int i0 = gtid; i0 < slice; i0 += U * gthreads) {
+        float4 ps[U][MAXP];
+        float pc[U][MAXP];
+        bool live[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * gthreads;
+            const long long k = (long long)P.rank * slice + i;
+            live[u] = i < slice && k < (long long)P.kcap;
+#pragma unroll
+            for (int p = 0; p < MAXP; ++p) {
+                if (p < P.world && live[u]) {
+                    const float *pa = reinterpret_cast<const float *>(P.peers[p] + aoff);
+                    ps[u][p] = ld_volatile_f4(reinterpret_cast<const float4 *>(pa) + k);
+                    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(pc[u][p]) : "l"(pa + (long long)P.kcap * 4 + k) : "memory");
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!live[u]) continue;
+            float4 s = ps[u][0];
+            float c = pc[u][0];
+#pragma unroll
+            for (int p = 1; p < MAXP; ++p)
+                if (p < P.world) { s.x += ps[u][p].x; s.y += ps[u][p].y; s.z += ps[u][p].z; s.w += ps[u][p].w; c += pc[u][p]; }
+            fz_rec_store(P.ws + P.ll_off + (long long)(i0 + u * gthreads) * 32, s, c, epoch);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -216,33 +313,51 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
     }
     __syncthreads();
     const unsigned epoch = *s_epoch;                 // 1-based index of this step
+    const unsigned fz_epoch_ = epoch;
+    FZ_TRACE(0);
+    if (tid == 0) {   // ring of per-step kernel start / end stamps on the GPU's global timer
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMin(reinterpret_cast<unsigned long long *>(P.ws + P.ctrl_off + 256) + (epoch & 31u) * 2, now);
+    }
     const unsigned target = epoch * gridDim.x;       // arrival count that completes this step's barriers
     const int par = (int)((epoch - 1u) & 1u);
     float *acc = reinterpret_cast<float *>(P.ws + (long long)par * P.accum_stride);
     float *cnt = acc + (long long)P.kcap * 4;
     const int n = P.h * P.w;
-    const int nitems = P.nrows * P.chunks;
+    const unsigned nitems = (unsigned)(P.nrows * P.chunks);
 
     // ------------------------------------------------------------------------------------------------- phase A
     if (warp == FZ_CONS) {
-        // producer
+        // producer.  Items (8 id rows x 32 cells) are dealt round-robin in CHUNK-MAJOR order (all rows of column chunk
+        // 0, then chunk 1, ...): an item's cost follows the number of entries in it, which varies mostly with the
+        // screen position, and the SM count is a multiple of the usual chunks-per-row, so a row-major deal would hand
+        // the same (busy or empty) screen column to one CTA every time.  (A ticket counter in L2 balances no better
+        // and serialises: ~7 ns per same-address atomic is as long as an item takes to stream.)
         uint64_t pol;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
         int stage = 0;
         unsigned ph = 0;
         const char *ids = reinterpret_cast<const char *>(P.ids);
         const XT *x = reinterpret_cast<const XT *>(P.x);
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        for (unsigned item = blockIdx.x;; item += gridDim.x) {
             mbar_wait(sbase + L::BAR_OFF + (FZ_STAGES + stage) * 8, ph ^ 1u);
-            const int row = item / P.chunks;
-            const int chunk = item - row * P.chunks;
+            const uint32_t sb = sbase + stage * L::STAGE;
+            const uint32_t full = sbase + L::BAR_OFF + stage * 8;
+            if (item >= nitems) {                    // end marker for the consumers
+                if (lane == 0) {
+                    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sb + L::DESC_OFF), "r"(0), "r"(-1) : "memory");
+                    mbar_arrive(full);
+                }
+                break;
+            }
+            const int chunk = (int)item / P.nrows;
+            const int row = (int)item - chunk * P.nrows;
             const int g = row / P.h;
             const int sy = row - g * P.h;
             const int fl = __ldg(P.fmap + g);
             const int sx0 = chunk * FZ_CELLS;
             const int ncell = min(FZ_CELLS, P.w - sx0);
-            const uint32_t sb = sbase + stage * L::STAGE;
-            const uint32_t full = sbase + L::BAR_OFF + stage * 8;
             if (lane == 0) {
                 asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sb + L::DESC_OFF), "r"((fl * P.h + sy) * P.w + sx0), "r"(ncell) : "memory");
                 mbar_expect_tx(full, (uint32_t)(ncell * (64 * FzId<IdT>::PX + 4 * (int)sizeof(XT))));
@@ -261,6 +376,13 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
     } else {
         // consumers: first clear the next step's accumulator and statistics while the first copies are in flight
         {
+            if (P.world > 1) {   // peers pulled from that accumulator during the previous step: wait until all are done
+                const unsigned done = (epoch - 1u) * gridDim.x;
+                for (int q = 0; q < P.world; ++q) {
+                    const unsigned *c = reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + 1 * SRX_MAX_PEERS + q;
+                    while ((int)(ld_relaxed(c, true) - done) < 0) { }
+                }
+            }
             float4 *other = reinterpret_cast<float4 *>(P.ws + (long long)(par ^ 1) * P.accum_stride);
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             const int stride = gridDim.x * FZ_CONS * 32;
@@ -272,10 +394,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         const uint32_t lane_off = r * FzId<IdT>::PITCH + pr * 2 * FzId<IdT>::PX;
         int stage = 0;
         unsigned ph = 0;
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        while (true) {
             mbar_wait(sbase + L::BAR_OFF + stage * 8, ph);
             const uint32_t sb = sbase + stage * L::STAGE;
             const int2 desc = lds64(sb + L::DESC_OFF);
+            if (desc.y < 0) break;                    // end marker
             int ka[FZ_CPW], kb[FZ_CPW];
             float xv[FZ_CPW][4];
 #pragma unroll
@@ -295,7 +418,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
 #pragma unroll
             for (int u = 0; u < FZ_CPW; ++u) {
                 const int cell = warp * FZ_CPW + u;
-                if (cell >= desc.y) break;            // warp-uniform (ragged last chunk of a row)
+                if (cell >= desc.y) break;            // warp-uniform
                 const int a = ka[u], b = kb[u];
                 const int hi = __reduce_max_sync(FULL, max(a, b));
                 if (hi < 0) {                         // no entry in this cell
@@ -317,7 +440,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
                         red_add_f32x4(acc + (long long)hi * 4, fm * xv[u][0], fm * xv[u][1], fm * xv[u][2], fm * xv[u][3]);
                         red_add_f32(cnt + hi, fm);
                     }
-                } else if (a == b) {                  // both valid (a >= 0 here, otherwise hi < 0 or a != b)
+                } else if (a == b) {                  // both valid and equal (a >= 0 here, otherwise hi < 0 or a != b)
                     if (a >= 0) {
                         red_add_f32x4(acc + (long long)a * 4, 2.f * xv[u][0], 2.f * xv[u][1], 2.f * xv[u][2], 2.f * xv[u][3]);
                         red_add_f32(cnt + a, 2.f);
@@ -337,106 +460,168 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
     }
 
     // ------------------------------------------------------------------------------------------------- barrier 0
+    FZ_TRACE(1);
     if (P.dbg & 4) {
         __syncthreads();
         if (blockIdx.x == 0 && tid == 0) *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off) = epoch;
         return;
     }
-    fz_barrier(P, 0, target, true);
+    fz_barrier(P, 0, target, true);    // every rank's reductions have landed in its own L2
+    FZ_TRACE(2);
+#define FZ_CTA_STAMP(idx)                                                                                          \
+    do {                                                                                                           \
+        if (tid == 0 && (epoch & 63u) == 40u) {                                                                    \
+            unsigned long long now_;                                                                               \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                                               \
+            reinterpret_cast<unsigned long long *>(P.ws + P.ctrl_off + 4096)[blockIdx.x * 3 + idx] = now_;          \
+        }                                                                                                          \
+    } while (0)
+    FZ_CTA_STAMP(0);
     if (blockIdx.x == 0 && tid == 0) *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off) = epoch;
 
     // ------------------------------------------------------------------------------------------------- phase X
-    if (P.world > 1) {
-        const int per = (P.accum_vec + P.world - 1) / P.world;
-        const int v0 = P.rank * per, v1 = min(P.accum_vec, v0 + per);
+    // Frame-sharded runs.  Rank r owns the slots [r*slice, (r+1)*slice): it PULLS the partial sums of its slice from
+    // every peer's accumulator (coalesced loads over NVLink), adds them in rank order and keeps the totals in its own
+    // memory as 32-byte records {sum.xyzw, count, step} written with one 256-bit store.  Phase B then fetches the
+    // winner's record from the owner (one 256-bit load, remote for foreign slots) and checks the step number inside it,
+    // so no second barrier is needed.  Nothing is ever stored to a peer except arrival counters: a system-scope fence
+    // behind remote stores costs ~6 us on this fabric, a pull costs one round trip (~2 us) — measured with
+    // tools/nvl_probe.py.
+    const bool xchg = P.world > 1;
+    const int slice = P.ll_slice;
+    if (xchg) {
+        const int gtid = blockIdx.x * FZ_THREADS + tid, gthreads = gridDim.x * FZ_THREADS;
         const long long aoff = (long long)par * P.accum_stride;
-        for (int v = v0 + blockIdx.x * FZ_THREADS + tid; v < v1; v += gridDim.x * FZ_THREADS) {
-            float4 part[SRX_MAX_PEERS];
-#pragma unroll
-            for (int p = 0; p < SRX_MAX_PEERS; ++p)
-                if (p < P.world) part[p] = ld_volatile_f4(reinterpret_cast<const float4 *>(P.peers[p] + aoff) + v);
-            float4 s = part[0];
-#pragma unroll
-            for (int p = 1; p < SRX_MAX_PEERS; ++p)
-                if (p < P.world) { s.x += part[p].x; s.y += part[p].y; s.z += part[p].z; s.w += part[p].w; }
-#pragma unroll
-            for (int p = 0; p < SRX_MAX_PEERS; ++p)
-                if (p < P.world) reinterpret_cast<float4 *>(P.peers[p] + aoff)[v] = s;
+        if (P.world <= 4) fz_pull_slice<2, 4>(P, acc, aoff, slice, epoch, gtid, gthreads);
+        else fz_pull_slice<1, SRX_MAX_PEERS>(P, acc, aoff, slice, epoch, gtid, gthreads);
+        FZ_TRACE(3);
+        // Tell every peer that this CTA (a) has stored its share of this rank's total records — the fence puts them in
+        // this GPU's L2 first — and (b) no longer reads the peer's accumulator of this step (peers clear it two steps on).
+        __threadfence();
+        __syncthreads();
+        if (tid < P.world)
+            red_relaxed_add(reinterpret_cast<unsigned *>(P.peers[tid] + P.pads_off) + 1 * SRX_MAX_PEERS + P.rank, 1u);
+        // ... and wait until every rank's records are complete: polling a record over NVLink before it is written costs
+        // a round trip per retry, polling these local counters costs nothing
+        if (tid < P.world) {
+            const unsigned *c = reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + 1 * SRX_MAX_PEERS + tid;
+            while ((int)(ld_relaxed(c, true) - target) < 0) { }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
-        fz_barrier(P, 1, target, true);
+        __syncthreads();
+        FZ_TRACE(4);
     }
+    FZ_CTA_STAMP(1);
 
-    // ------------------------------------------------------------------------------------------------- phase B
+    // ------------------------------------------------------------------------------------------------- phases B, C
+    // Each latent frame is handled by a group of `grp` CTAs (grp = gridDim / frames when there are fewer frames than
+    // CTAs, else 1 and a CTA walks over several frames).  Only the CTAs of one frame exchange statistics, through
+    // that frame's own arrival counter, so no grid-wide barrier separates gather and AdaIN.
     XT *x = reinterpret_cast<XT *>(P.x);
-    const long long total = (long long)P.batch * n;
-    const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
-    const long long c0 = min(total, (long long)blockIdx.x * per_cta), c1 = min(total, c0 + per_cta);
     double *red = reinterpret_cast<double *>(smem + L::RED_OFF);
     float *coef = reinterpret_cast<float *>(smem + L::COEF_OFF);
     double *stats = reinterpret_cast<double *>(P.ws + P.stats_off) + (long long)par * P.batch * 16;
-    const int f_lo = (int)(c0 / n), f_hi = c1 > c0 ? (int)((c1 - 1) / n) : f_lo - 1;
-
-    for (int f = f_lo; f <= f_hi; ++f) {
-        const int s0 = (int)(max(c0, (long long)f * n) - (long long)f * n);
-        const int s1 = (int)(min(c1, (long long)(f + 1) * n) - (long long)f * n);
+    unsigned *fcount = reinterpret_cast<unsigned *>(P.ws + P.stats_off + (long long)2 * P.batch * 128);
+    const int G = gridDim.x;
+    const int grp = P.batch >= G ? 1 : G / P.batch;
+    const int f_first = grp == 1 ? (int)blockIdx.x : (int)blockIdx.x / grp;
+    const int f_step = grp == 1 ? G : P.batch;          // grouped CTAs handle exactly one frame
+    const int part = grp == 1 ? 0 : (int)blockIdx.x % grp;
+    for (int f = f_first; f < P.batch; f += f_step) {
+        const int s0 = (int)((long long)n * part / grp), s1 = (int)((long long)n * (part + 1) / grp);
         XT *xf = x + (long long)f * 4 * n;
         const int *wf = P.winner + (long long)f * n;
         double sums[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) sums[j] = 0.0;
-        for (int ci = s0 + tid; ci < s1; ci += FZ_THREADS) {
-            const int slot = __ldcg(wf + ci);
-            float xv[4], bv[4];
+        for (int c0 = s0 + tid; c0 < s1; c0 += FZ_BU * FZ_THREADS) {
+            // FZ_BU cells per thread per round, loads grouped by dependency level (winner -> accumulator) so that a
+            // round costs two L2 round trips instead of 2 * FZ_BU
+            int slot[FZ_BU];
+            float xv[FZ_BU][4];
+            float4 a[FZ_BU];
+            float cn[FZ_BU];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) xv[ch] = XIo<XT>::ld(xf + (long long)ch * n + ci);
-            if (slot >= 0) {
-                const float4 a = __ldcg(reinterpret_cast<const float4 *>(acc) + slot);
-                const float cn = __ldcg(cnt + slot);
-                // mean, then (1-r)*x + r*m : mul, mul, add, each rounded (corresponder.py:351-352)
-                bv[0] = __fadd_rn(__fmul_rn(P.one_minus, xv[0]), __fmul_rn(P.ratio, __fdiv_rn(a.x, cn)));
-                bv[1] = __fadd_rn(__fmul_rn(P.one_minus, xv[1]), __fmul_rn(P.ratio, __fdiv_rn(a.y, cn)));
-                bv[2] = __fadd_rn(__fmul_rn(P.one_minus, xv[2]), __fmul_rn(P.ratio, __fdiv_rn(a.z, cn)));
-                bv[3] = __fadd_rn(__fmul_rn(P.one_minus, xv[3]), __fmul_rn(P.ratio, __fdiv_rn(a.w, cn)));
-                if (!P.adain) {
+            for (int u = 0; u < FZ_BU; ++u) {
+                const int ci = c0 + u * FZ_THREADS;
+                slot[u] = ci < s1 ? __ldcg(wf + ci) : -2;
+            }
 #pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) XIo<XT>::st(xf + (long long)ch * n + ci, bv[ch]);
+            for (int u = 0; u < FZ_BU; ++u) {
+                const int ci = min(c0 + u * FZ_THREADS, s1 - 1);
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) xv[u][ch] = XIo<XT>::ld(xf + (long long)ch * n + ci);
+            }
+#pragma unroll
+            for (int u = 0; u < FZ_BU; ++u) {
+                a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                cn[u] = 1.f;
+                if (slot[u] >= 0) {
+                    if (xchg) {                       // the owner's record of this step (remote for foreign slots)
+                        const int o = slot[u] / slice;
+                        const FzRec r = fz_rec_wait(P.peers[o] + P.ll_off + (long long)(slot[u] - o * slice) * 32, epoch);
+                        a[u] = r.s;
+                        cn[u] = r.c;
+                    } else {
+                        a[u] = __ldcg(reinterpret_cast<const float4 *>(acc) + slot[u]);
+                        cn[u] = __ldcg(cnt + slot[u]);
+                    }
                 }
-            } else {
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) bv[ch] = xv[ch];
             }
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const double dx = xv[ch], db = bv[ch];
-                sums[ch * 4 + 0] += dx; sums[ch * 4 + 1] += dx * dx; sums[ch * 4 + 2] += db; sums[ch * 4 + 3] += db * db;
+            for (int u = 0; u < FZ_BU; ++u) {
+                if (slot[u] == -2) continue;
+                const int ci = c0 + u * FZ_THREADS;
+                float bv[4];
+                if (slot[u] >= 0) {
+                    // mean, then (1-r)*x + r*m : mul, mul, add, each rounded (corresponder.py:351-352)
+                    bv[0] = __fadd_rn(__fmul_rn(P.one_minus, xv[u][0]), __fmul_rn(P.ratio, __fdiv_rn(a[u].x, cn[u])));
+                    bv[1] = __fadd_rn(__fmul_rn(P.one_minus, xv[u][1]), __fmul_rn(P.ratio, __fdiv_rn(a[u].y, cn[u])));
+                    bv[2] = __fadd_rn(__fmul_rn(P.one_minus, xv[u][2]), __fmul_rn(P.ratio, __fdiv_rn(a[u].z, cn[u])));
+                    bv[3] = __fadd_rn(__fmul_rn(P.one_minus, xv[u][3]), __fmul_rn(P.ratio, __fdiv_rn(a[u].w, cn[u])));
+                    if (!P.adain) {
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch) XIo<XT>::st(xf + (long long)ch * n + ci, bv[ch]);
+                    }
+                } else {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) bv[ch] = xv[u][ch];
+                }
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    const double dx = xv[u][ch], db = bv[ch];
+                    sums[ch * 4 + 0] += dx; sums[ch * 4 + 1] += dx * dx; sums[ch * 4 + 2] += db; sums[ch * 4 + 3] += db * db;
+                }
             }
         }
-        if (P.adain) {
+        if (!P.adain) continue;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const double v = fz_warp_sum(sums[j]);
-                if (lane == 0) red[warp * 16 + j] = v;
-            }
-            __syncthreads();
-            if (tid < 16) {
-                double v = 0.0;
-                for (int k = 0; k < FZ_THREADS / 32; ++k) v += red[k * 16 + tid];
-                atomicAdd(stats + (long long)f * 16 + tid, v);
-            }
-            __syncthreads();
+        for (int j = 0; j < 16; ++j) {
+            const double v = fz_warp_sum(sums[j]);
+            if (lane == 0) red[warp * 16 + j] = v;
         }
-    }
-    if (!P.adain) return;
-
-    // ------------------------------------------------------------------------------------------------- phase C
-    fz_barrier(P, 2, target, false);
-    for (int f = f_lo; f <= f_hi; ++f) {
-        const int s0 = (int)(max(c0, (long long)f * n) - (long long)f * n);
-        const int s1 = (int)(min(c1, (long long)(f + 1) * n) - (long long)f * n);
-        XT *xf = x + (long long)f * 4 * n;
+        __syncthreads();
+        double *fs = stats + (long long)f * 16;
+        if (tid < 16) {
+            double v = 0.0;
+            for (int k = 0; k < FZ_THREADS / 32; ++k) v += red[k * 16 + tid];
+            if (grp > 1) atomicAdd(fs + tid, v);
+            else red[tid] = v;                         // warp 0 only reads rows written before the barrier above
+        }
+        if (grp > 1) {                                 // the frame's CTAs meet at the frame's own counter
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                red_release_add(fcount + f, 1u, false);
+                const unsigned tgt = epoch * (unsigned)grp;
+                while ((int)(ld_acquire(fcount + f, false) - tgt) < 0) { }
+            }
+        }
+        __syncthreads();
         if (tid < 4) {
-            const double *s = stats + (long long)f * 16 + tid * 4;
-            const double sx = __ldcg(s), sxx = __ldcg(s + 1), sb = __ldcg(s + 2), sbb = __ldcg(s + 3);
+            double sx, sxx, sb, sbb;
+            if (grp > 1) { sx = __ldcg(fs + tid * 4); sxx = __ldcg(fs + tid * 4 + 1); sb = __ldcg(fs + tid * 4 + 2); sbb = __ldcg(fs + tid * 4 + 3); }
+            else { sx = red[tid * 4]; sxx = red[tid * 4 + 1]; sb = red[tid * 4 + 2]; sbb = red[tid * 4 + 3]; }
             const double dn = (double)n;
             // unbiased variance + 1e-5, sqrt (math_utils.py:39-47)
             coef[tid * 4 + 0] = (float)(sx / dn);
@@ -445,6 +630,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             coef[tid * 4 + 3] = (float)(sb / dn);
         }
         __syncthreads();
+#pragma unroll 4
         for (int ci = s0 + tid; ci < s1; ci += FZ_THREADS) {
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
@@ -456,6 +642,18 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             }
         }
         __syncthreads();
+    }
+    FZ_TRACE(7);
+    FZ_CTA_STAMP(2);
+    if (tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        unsigned long long *ring = reinterpret_cast<unsigned long long *>(P.ws + P.ctrl_off + 256);
+        atomicMax(ring + (epoch & 31u) * 2 + 1, now);
+        if (blockIdx.x == 0) {   // prepare the slot of the step after next
+            ring[((epoch + 2u) & 31u) * 2] = ~0ull;
+            ring[((epoch + 2u) & 31u) * 2 + 1] = 0ull;
+        }
     }
 }
 
@@ -503,6 +701,8 @@ static int launch_fused_t(srx_plan *p, const srx_step_args *a, cudaStream_t st) 
     P.ws = p->ws;
     for (int i = 0; i < SRX_MAX_PEERS; ++i) P.peers[i] = p->world > 1 ? p->peers[i] : nullptr;
     P.peers[p->world > 1 ? p->rank : 0] = p->ws;
+    P.ll_off = p->ll_off;
+    P.ll_slice = (int)((p->kcap + p->world - 1) / p->world);
     P.accum_stride = p->accum_stride;
     P.pads_off = p->pads_off;
     P.ctrl_off = p->ctrl_off;
@@ -535,7 +735,9 @@ static int launch_fused_t(srx_plan *p, const srx_step_args *a, cudaStream_t st) 
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static int coop = -1;
+    if (coop < 0) { const char *e = getenv("SRX_FZ_COOP"); coop = (e && e[0] == '0') ? 0 : 1; }
+    cfg.numAttrs = coop ? 1 : 0;
     SRX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, P));
     return SRX_OK;
 }
@@ -577,5 +779,28 @@ extern "C" int srx_plan_set_grid(srx_plan *p, int ctas) {
     SRX_REQUIRE(p, SRX_ERR_INVALID, "null plan");
     SRX_REQUIRE(ctas >= 0 && ctas <= srx_sm_count_cached(), SRX_ERR_INVALID, "grid must be between 0 and the SM count");
     p->fused_grid = ctas;
+    return SRX_OK;
+}
+
+// Phase timestamps of the last step (SM clock ticks relative to kernel entry): out[0..7] first CTA, out[8..15] last CTA.
+// Indices: 0 entry, 1 phase A done, 2 barrier 0 passed, 3 exchange done, 4 barrier 1 passed, 7 exit (5, 6 unused).  Syncs the stream.  Profiling aid.
+extern "C" int srx_plan_read_trace(srx_plan *p, int64_t *out16, void *stream) {
+    SRX_REQUIRE(p && p->ws && out16, SRX_ERR_INVALID, "null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (out16 == reinterpret_cast<int64_t *>(-1)) return SRX_ERR_INVALID;
+    SRX_CUDA_CHECK(cudaMemcpyAsync(out16, p->ws + p->ctrl_off + 64, 128, cudaMemcpyDeviceToHost, st));
+    SRX_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SRX_OK;
+}
+
+// Profiling aid: ring of the last 32 steps' (earliest CTA start, latest CTA end) on the GPU global timer [ns], slot = step & 31,
+// followed by the first CTA's 8 phase stamps (SM clock) of each of those steps: out64[64 + 8 * slot + idx].
+extern "C" int srx_plan_read_step_ring(srx_plan *p, uint64_t *out64, void *stream) {
+    SRX_REQUIRE(p && p->ws && out64, SRX_ERR_INVALID, "null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SRX_CUDA_CHECK(cudaMemcpyAsync(out64, p->ws + p->ctrl_off + 256, 512, cudaMemcpyDeviceToHost, st));
+    SRX_CUDA_CHECK(cudaMemcpyAsync(out64 + 64, p->ws + p->ctrl_off + 1024, 2048, cudaMemcpyDeviceToHost, st));
+    SRX_CUDA_CHECK(cudaMemcpyAsync(out64 + 320, p->ws + p->ctrl_off + 4096, 148 * 3 * 8, cudaMemcpyDeviceToHost, st));
+    SRX_CUDA_CHECK(cudaStreamSynchronize(st));
     return SRX_OK;
 }

@@ -597,7 +597,8 @@ extern "C" int srx_plan_bind_workspace(srx_plan *p, void *ws, int64_t bytes, voi
     p->ws = reinterpret_cast<char *>(ws);
     p->ws_bytes = bytes;
     // accumulator starts clean; latent frames that no id frame maps to keep winner = -1 forever
-    SRX_CUDA_CHECK(cudaMemsetAsync(p->ws, 0, (size_t)(3 * p->accum_stride + 512), st));   // A0, A1, A2, pads, ctrl
+    // A0, A1, A2, pads, ctrl, exchange records (their flags must start below step 1)
+    SRX_CUDA_CHECK(cudaMemsetAsync(p->ws, 0, (size_t)(p->ll_off + p->ll_bytes), st));
     SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->stats_off, 0, (size_t)p->stats_bytes, st));
     SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->winner_off, 0xFF, p->winner_bytes, st));
     SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->status_off, 0, 256, st));

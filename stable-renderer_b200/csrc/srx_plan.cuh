@@ -19,7 +19,7 @@ struct srx_plan {
     int elem = 4;
     int cluster = 1;
     // frame-sharded peer mode (srx_plan_bind_peers): double-buffered accumulators + signal pads inside the workspace
-    int64_t accum_stride = 0, pads_off = 0, ctrl_off = 0, stats_off = 0, stats_bytes = 0;
+    int64_t accum_stride = 0, pads_off = 0, ctrl_off = 0, stats_off = 0, stats_bytes = 0, ll_off = 0, ll_bytes = 0;
     int world = 1, rank = 0;
     char *peers[SRX_MAX_PEERS] = {nullptr};
     int fused_grid = 0;   // CTAs of the persistent kernel; 0 = one per SM
@@ -44,8 +44,12 @@ static inline void plan_layout(srx_plan *p) {
     off += p->accum_stride;
     p->pads_off = off;   // [3 barriers][SRX_MAX_PEERS sources] u32 arrival counters (monotonic)
     off += 256;
-    p->ctrl_off = off;   // [0] step counter
-    off += 256;
+    p->ctrl_off = off;   // [0] step counter; +64 phase stamps of the first / last CTA; +256 ring of per-step (first CTA
+    off += 8192;         // start, last CTA end) global-timer stamps; +1024 ring of the first CTA's phase stamps (profiling aids)
+    // peer mode: this rank's slice of exchanged totals, [ceil(K / world)] records of 32 B {sum.xyzw, count, step}; world >= 2
+    p->ll_off = off;
+    p->ll_bytes = p->fused ? (p->kcap / 2 + 64) * 32 : 0;
+    off = align_up(off + p->ll_bytes, 256);
     p->winner_off = off;
     p->winner_bytes = (int64_t)d.batch * d.lat_h * d.lat_w * 4;
     off = align_up(off + p->winner_bytes, 256);
@@ -54,8 +58,9 @@ static inline void plan_layout(srx_plan *p) {
     off = align_up(off + p->winner64_bytes, 256);
     p->status_off = off;
     off += 256;
-    p->stats_off = off;  // [2][batch][16] double: per-frame AdaIN sums of the persistent step kernel (double buffered)
-    p->stats_bytes = (int64_t)2 * d.batch * 16 * 8;
+    p->stats_off = off;  // [2][batch][16] double: per-frame AdaIN sums of the persistent step kernel (double buffered),
+                         // then [batch] u32 per-frame arrival counters (monotonic)
+    p->stats_bytes = (int64_t)2 * d.batch * 16 * 8 + (int64_t)d.batch * 4;
     off = align_up(off + p->stats_bytes, 256);
     p->total_bytes = off;
 }

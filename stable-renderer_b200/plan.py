@@ -6,6 +6,7 @@ materialised: keying happens inside the streaming kernel."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -128,6 +129,19 @@ class OverlapPlan:
         arr = (C.c_void_p * world)(*[int(v) for v in peer_workspaces])
         _lib.check(_lib.load().srx_plan_bind_peers(self._handle, int(rank), world, arr))
         self.world, self.exchange = world, ("peer" if world > 1 else "none")
+
+    def read_trace(self) -> dict:
+        """Phase durations (microseconds at `sm_mhz`-independent SM ticks -> caller scales) of the last persistent step."""
+        buf = (C.c_int64 * 16)()
+        _lib.check(_lib.load().srx_plan_read_trace(self._handle, buf, _lib.current_stream_ptr(self.device)))
+        v = list(buf)
+        return {"first_cta": v[:8], "last_cta": v[8:]}
+
+    def read_step_ring(self) -> list:
+        buf = (C.c_uint64 * (320 + 148 * 3))()
+        _lib.check(_lib.load().srx_plan_read_step_ring(self._handle, buf, _lib.current_stream_ptr(self.device)))
+        self.cta_stamps = [[int(buf[320 + 3 * i + j]) for j in range(3)] for i in range(148)]
+        return [(int(buf[2 * i]), int(buf[2 * i + 1]), [int(buf[64 + 8 * i + j]) for j in range(8)]) for i in range(32)]
 
     def set_grid(self, ctas: int) -> None:
         _lib.check(_lib.load().srx_plan_set_grid(self._handle, int(ctas)))

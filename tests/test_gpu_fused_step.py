@@ -149,3 +149,26 @@ def test_fused_peer_exchange_two_gpus():
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
     assert "PEER_OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
+
+
+def test_fused_large_vertex_ids_round_like_float32():
+    """Vertex ids in [2^24, 2^25) are not exact in the reference's float32 rows (corrmap.py:256-261): neighbours collapse
+    onto one key.  The persistent kernel rounds in integer arithmetic; the split kernels convert through float."""
+    from stable_renderer_b200.plan import OverlapPlan
+    H = 64
+    gen = torch.Generator().manual_seed(5)
+    ids = torch.zeros(2, H, H, 4, dtype=torch.int32)
+    ids[..., 0] = 1
+    ids[..., 3] = (1 << 24) - 40 + torch.randint(0, 200, (2, H, H), generator=gen, dtype=torch.int32)
+    x0 = torch.randn(2, 4, 8, 8, generator=gen)
+    want = O.overlap_step(x0.numpy(), ids.numpy(), None, ratio=0.5, accumulate="f64")
+    cap = (1 << 24) + 256
+    a, b = x0.cuda(), x0.cuda()
+    pf = OverlapPlan(ids.cuda(), a.shape, key_capacity=cap)
+    ps = OverlapPlan(ids.cuda(), b.shape, key_capacity=cap, split_kernels=True)
+    assert pf.fused and not ps.fused
+    pf.step(a, 0.5)
+    ps.step(b, 0.5)
+    pf.check()
+    assert_close(t2n(a), want, RTOL, ATOL, "fused, ids around 2^24")
+    assert_close(t2n(b), want, RTOL, ATOL, "split, ids around 2^24")
