@@ -101,6 +101,9 @@ typedef struct srx_plan_info {
     int accum_dtype;         /* SRX_F32 (fast) — int64 in deterministic mode is reported as -64 */
     int fast_path;           /* 1 when the 8x8-pixels-per-cell warp kernel applies */
     int fused;               /* 1 when srx_overlap_step runs as the single persistent kernel (and peer mode is available) */
+    int64_t need_offset;     /* byte offset inside the workspace of the [key_capacity] byte map "key wins a cell", written by
+                                the first call of srx_plan_build_cache; frame-sharded callers MAX-all-reduce it across ranks
+                                before the second call (a key matters if it wins a cell on ANY rank) */
 } srx_plan_info;
 
 /* Builds the plan for one batch of id buffers.  `ids_dev` may be NULL when key_capacity > 0 (ids are then given to
@@ -115,6 +118,15 @@ int srx_plan_bind_workspace(srx_plan *plan, void *workspace_dev, int64_t bytes, 
  * frames, exchanges the key accumulator with the peers over NVLink inside the same kernel, and gathers this rank's
  * frames; every rank must call it the same number of times.  world = 1 unbinds. */
 int srx_plan_bind_peers(srx_plan *plan, int rank, int world, void *const *peer_workspaces);
+/* Bucketing pass for the cached-plan regime (steps 2..N of a sampling run reuse the ids).  Replaces what the
+ * reference recomputes every step — `unique(return_inverse)` over the [N] key column (math_utils.py:137) — by one pass
+ * per id batch.  Call twice: with pool_dev == NULL it streams the ids once (per-cell winners, the set of keys that win a
+ * cell, pairs per CTA), SYNCS, and returns in *pool_bytes the pool size to allocate; with pool_dev it streams the ids again
+ * and stores the (key, cell, multiplicity) pairs of the keys that matter.  The pool must stay alive while cached steps run.
+ * Frame-sharded runs combine the ranks' key maps between the two calls (srx_plan_info.need_offset). */
+int srx_plan_build_cache(srx_plan *plan, const void *ids_dev, void *pool_dev, int64_t *pool_bytes, void *stream);
+/* pairs kept / pairs seen by the last build (syncs) */
+int srx_plan_cache_entries(srx_plan *plan, int64_t *kept, int64_t *capacity, void *stream);
 /* CTAs of the persistent step kernel (default 0 = one per SM).  Every rank of a peer group must use the same value;
  * smaller grids let several ranks' kernels share one GPU (single-GPU emulation of a frame-sharded run in the tests). */
 int srx_plan_set_grid(srx_plan *plan, int ctas);
@@ -144,10 +156,11 @@ int srx_vertex_screen_info(const void *ids_dev, int id_dtype, int frames, int he
 typedef struct srx_step_args {
     void *x_dev;             /* latents [B,C,h,w], contiguous, updated in place */
     int x_dtype;             /* SRX_F32 | SRX_F16 | SRX_BF16 */
-    const void *ids_dev;     /* id buffers [F,H,W,4] of this step (streaming regime); NULL = use the plan's cached slots */
+    const void *ids_dev;     /* id buffers [F,H,W,4] of this step (streaming regime); NULL = cached-plan regime: run from the
+                                pairs stored by srx_plan_build_cache (same ids for every denoise step of a sampling run) */
     float ratio;             /* step_finished_inject_ratio (corresponder.py:180,351-352) */
     int adain;               /* 1 = reference behaviour (re-standardise the original latents); 0 = write the blend */
-    int cache_slots;         /* 1 = also record the per-pixel slot map so later steps can pass ids_dev = NULL */
+    int cache_slots;         /* reserved, must be 0 */
 } srx_step_args;
 
 /* reduce + gather on one GPU */

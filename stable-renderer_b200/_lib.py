@@ -38,7 +38,7 @@ class srx_plan_desc(C.Structure):
 class srx_plan_info(C.Structure):
     _fields_ = [("n_valid", C.c_int64), ("key_min", C.c_int64), ("key_max", C.c_int64), ("key_capacity", C.c_int64),
                 ("workspace_bytes", C.c_int64), ("accum_offset", C.c_int64), ("accum_bytes", C.c_int64),
-                ("accum_dtype", C.c_int), ("fast_path", C.c_int), ("fused", C.c_int)]
+                ("accum_dtype", C.c_int), ("fast_path", C.c_int), ("fused", C.c_int), ("need_offset", C.c_int64)]
 
 
 class srx_step_args(C.Structure):
@@ -75,6 +75,8 @@ _PROTOTYPES = {
     "srx_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(srx_plan_info)]),
     "srx_plan_bind_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "srx_plan_bind_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "srx_plan_build_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "srx_plan_cache_entries": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]),
     "srx_plan_set_grid": (C.c_int, [C.c_void_p, C.c_int]),
     "srx_plan_read_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "srx_plan_read_step_ring": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),

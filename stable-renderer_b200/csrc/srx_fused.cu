@@ -22,6 +22,7 @@
 // kernel replays unchanged from a CUDA graph); the launch is cooperative so that all CTAs are co-resident.
 #include "srx_plan.cuh"
 #include <stdlib.h>
+#include <vector>
 
 #define FZ_CONS 16                        // consumer warps
 #define FZ_THREADS ((FZ_CONS + 1) * 32)   // + one producer warp
@@ -32,6 +33,13 @@
 #define FZ_BU 2                           // cells per thread per round of the gather phase
 
 enum { FZ_ST_KEY_RANGE = 0 };
+// What the kernel does with the ids:
+//   STEP    the streaming overlap step (ids new for this call)
+//   MARK    bucketing pass 1 — phase A only: winners, the bitmap of winner keys, pairs per CTA.  No reductions.
+//   EMIT    bucketing pass 2 — phase A only: every CTA appends the (key, cell, multiplicity) pairs whose key is in the
+//           bitmap to its own region of the pool (same static deal of items as MARK, so the MARK counts bound the regions)
+//   CACHED  the overlap step from the pool: no id traffic; reductions only for keys that matter
+enum { FZ_MODE_STEP = 0, FZ_MODE_MARK = 1, FZ_MODE_EMIT = 2, FZ_MODE_CACHED = 3 };
 
 template <typename IdT> struct FzId;
 // row pitch = row bytes + a skew that makes the consumers' 128-bit shared loads bank-conflict free
@@ -69,6 +77,10 @@ struct FzParams {
     int adain;
     int world, rank;
     int accum_vec;            // float4 vectors in one accumulator (sums then counts)
+    int mode;                 // FZ_MODE_*
+    unsigned char *need;      // [kcap] 1 = the key wins some cell on some rank (the only keys whose mean is ever read)
+    int *cta_tab;             // [3][gridDim]: pairs seen by each CTA (MARK), entries kept (EMIT), first entry of its region
+    int2 *pool;               // cached plan: (slot, cell << 6 | multiplicity - 1) entries, one region per CTA
     int dbg;                  // SRX_FZ_DEBUG experiment bits (results are wrong when set): 1 = no reductions,
                               // 2 = consumers only drain the ring, 4 = stop after phase A
 };
@@ -269,23 +281,40 @@ __device__ __forceinline__ void fz_pull_slice(const FzParams &P, const float *ac
             const int i = i0 + u * gthreads;
             const long long k = (long long)P.rank * slice + i;
             live[u] = i < slice && k < (long long)P.kcap;
+            // ring order starting at this rank's neighbour: at any moment the ranks read from different peers
+            // (array index j = ring position; the sum below still runs in rank order)
 #pragma unroll
-            for (int p = 0; p < MAXP; ++p) {
-                if (p < P.world && live[u]) {
+            for (int j = 0; j < MAXP; ++j) {
+                if (j < P.world && live[u]) {
+                    int p = P.rank + 1 + j;
+                    if (p >= P.world) p -= P.world;
                     const float *pa = reinterpret_cast<const float *>(P.peers[p] + aoff);
-                    ps[u][p] = ld_volatile_f4(reinterpret_cast<const float4 *>(pa) + k);
-                    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(pc[u][p]) : "l"(pa + (long long)P.kcap * 4 + k) : "memory");
+                    ps[u][j] = ld_volatile_f4(reinterpret_cast<const float4 *>(pa) + k);
+                    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(pc[u][j]) : "l"(pa + (long long)P.kcap * 4 + k) : "memory");
                 }
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (!live[u]) continue;
-            float4 s = ps[u][0];
-            float c = pc[u][0];
+            // rank p sits at ring position j = p - rank - 1 (mod world); add in rank order so that the total does not
+            // depend on which rank owns the slot
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            float c = 0.f;
 #pragma unroll
-            for (int p = 1; p < MAXP; ++p)
-                if (p < P.world) { s.x += ps[u][p].x; s.y += ps[u][p].y; s.z += ps[u][p].z; s.w += ps[u][p].w; c += pc[u][p]; }
+            for (int p = 0; p < MAXP; ++p) {
+                if (p < P.world) {
+                    int j = p - P.rank - 1;
+                    if (j < 0) j += P.world;
+                    float4 v = ps[u][0];
+                    float vc = pc[u][0];
+#pragma unroll
+                    for (int q = 1; q < MAXP; ++q)
+                        if (q == j) { v = ps[u][q]; vc = pc[u][q]; }
+                    if (p == 0) { s = v; c = vc; }
+                    else { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; c += vc; }
+                }
+            }
             fz_rec_store(P.ws + P.ll_off + (long long)(i0 + u * gthreads) * 32, s, c, epoch);
         }
     }
@@ -310,6 +339,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *s_epoch = *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off) + 1u;
+        *reinterpret_cast<volatile unsigned *>(smem + L::MISC_OFF + 4) = 0u;
     }
     __syncthreads();
     const unsigned epoch = *s_epoch;                 // 1-based index of this step
@@ -328,7 +358,40 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
     const unsigned nitems = (unsigned)(P.nrows * P.chunks);
 
     // ------------------------------------------------------------------------------------------------- phase A
-    if (warp == FZ_CONS) {
+    const bool with_x = P.mode == FZ_MODE_STEP;
+    unsigned *s_fill = reinterpret_cast<unsigned *>(smem + L::MISC_OFF + 4);   // pairs / entries of this CTA
+    if (P.mode == FZ_MODE_CACHED) {
+        // cached plan: this CTA's region of the pool, all warps
+        if (warp != FZ_CONS) {
+            float4 *other = reinterpret_cast<float4 *>(P.ws + (long long)(par ^ 1) * P.accum_stride);
+            if (P.world > 1) {
+                const unsigned done = (epoch - 1u) * gridDim.x;
+                for (int q = 0; q < P.world; ++q) {
+                    const unsigned *c = reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + 1 * SRX_MAX_PEERS + q;
+                    while ((int)(ld_relaxed(c, true) - done) < 0) { }
+                }
+            }
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int stride = gridDim.x * FZ_CONS * 32;
+            for (int v = blockIdx.x * FZ_CONS * 32 + tid; v < P.accum_vec; v += stride) other[v] = z;
+            float4 *st_other = reinterpret_cast<float4 *>(P.ws + P.stats_off + (long long)(par ^ 1) * P.batch * 128);
+            for (int v = blockIdx.x * FZ_CONS * 32 + tid; v < P.batch * 8; v += stride) st_other[v] = z;
+        }
+        const int G = gridDim.x;
+        const int e0 = P.cta_tab[2 * G + blockIdx.x], e1 = e0 + P.cta_tab[G + blockIdx.x];
+        const XT *xs = reinterpret_cast<const XT *>(P.x);
+        for (int e = e0 + tid; e < e1; e += FZ_THREADS) {
+            const int2 en = __ldg(P.pool + e);
+            const unsigned cc = (unsigned)en.y;
+            const int cell = (int)(cc >> 6);
+            const float fm = (float)((cc & 63u) + 1u);
+            const int fr = cell / n, ci = cell - fr * n;
+            const XT *xp = xs + (long long)fr * 4 * n + ci;
+            const float x0 = XIo<XT>::ld(xp), x1 = XIo<XT>::ld(xp + n), x2 = XIo<XT>::ld(xp + 2 * n), x3 = XIo<XT>::ld(xp + 3 * n);
+            red_add_f32x4(acc + (long long)en.x * 4, fm * x0, fm * x1, fm * x2, fm * x3);
+            red_add_f32(cnt + en.x, fm);
+        }
+    } else if (warp == FZ_CONS) {
         // producer.  Items (8 id rows x 32 cells) are dealt round-robin in CHUNK-MAJOR order (all rows of column chunk
         // 0, then chunk 1, ...): an item's cost follows the number of entries in it, which varies mostly with the
         // screen position, and the SM count is a multiple of the usual chunks-per-row, so a row-major deal would hand
@@ -360,13 +423,13 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             const int ncell = min(FZ_CELLS, P.w - sx0);
             if (lane == 0) {
                 asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sb + L::DESC_OFF), "r"((fl * P.h + sy) * P.w + sx0), "r"(ncell) : "memory");
-                mbar_expect_tx(full, (uint32_t)(ncell * (64 * FzId<IdT>::PX + 4 * (int)sizeof(XT))));
+                mbar_expect_tx(full, (uint32_t)(ncell * (64 * FzId<IdT>::PX + (with_x ? 4 * (int)sizeof(XT) : 0))));
             }
             __syncwarp();
             if (lane < 8) {
                 const long long px = ((long long)g * P.H + sy * 8 + lane) * P.W + sx0 * 8;
                 bulk_g2s_hint(sb + lane * FzId<IdT>::PITCH, ids + px * FzId<IdT>::PX, (uint32_t)(ncell * 8 * FzId<IdT>::PX), full, pol);
-            } else if (lane < 12) {
+            } else if (lane < 12 && with_x) {
                 const int ch = lane - 8;
                 bulk_g2s(sb + L::LAT_OFF + ch * FZ_CELLS * (int)sizeof(XT),
                          x + ((long long)(fl * 4 + ch) * P.h + sy) * P.w + sx0, (uint32_t)(ncell * (int)sizeof(XT)), full);
@@ -375,7 +438,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         }
     } else {
         // consumers: first clear the next step's accumulator and statistics while the first copies are in flight
-        {
+        if (P.mode == FZ_MODE_STEP) {
             if (P.world > 1) {   // peers pulled from that accumulator during the previous step: wait until all are done
                 const unsigned done = (epoch - 1u) * gridDim.x;
                 for (int q = 0; q < P.world; ++q) {
@@ -433,6 +496,40 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
                 if (lane == 0) P.winner[desc.x + cell] = (int)(wp & ((1u << FZ_SLOT_BITS) - 1u));
                 const unsigned lo = __reduce_min_sync(FULL, min((unsigned)a, (unsigned)b));
                 if (P.dbg & 1) continue;
+                if (P.mode != FZ_MODE_STEP) {
+                    // bucketing passes: the same reduce-by-key, but the (key, multiplicity) pairs are counted / stored
+                    const bool single = (int)lo == hi;
+                    const bool same = a == b;
+                    int ka1 = a, kb1 = same ? -1 : b, ma = same ? 2 : 1;
+                    if (single) {
+                        const int total = __reduce_add_sync(FULL, (a >= 0) + (b >= 0));
+                        ka1 = lane == 0 ? hi : -1;
+                        kb1 = -1;
+                        ma = total;
+                    }
+                    if (P.mode == FZ_MODE_MARK) {
+                        const int w = (int)(wp & ((1u << FZ_SLOT_BITS) - 1u));
+                        const int np = __popc(__ballot_sync(FULL, ka1 >= 0)) + __popc(__ballot_sync(FULL, kb1 >= 0));
+                        if (lane == 0) {
+                            P.need[w] = 1;
+                            atomicAdd(s_fill, (unsigned)np);
+                        }
+                    } else {   // EMIT
+                        const bool fa = ka1 >= 0 && __ldg(P.need + ka1) != 0;
+                        const bool fb = kb1 >= 0 && __ldg(P.need + kb1) != 0;
+                        const unsigned ba = __ballot_sync(FULL, fa), bb = __ballot_sync(FULL, fb);
+                        const int tot = __popc(ba) + __popc(bb);
+                        unsigned base = 0;
+                        if (lane == 0 && tot) base = atomicAdd(s_fill, (unsigned)tot);
+                        base = __shfl_sync(FULL, base, 0);
+                        const unsigned lt = (1u << lane) - 1u;
+                        const unsigned cellg = (unsigned)(desc.x + cell) << 6;
+                        int2 *dst = P.pool + P.cta_tab[2 * gridDim.x + blockIdx.x] + base;
+                        if (fa) dst[__popc(ba & lt)] = make_int2(ka1, (int)(cellg | (unsigned)(ma - 1)));
+                        if (fb) dst[__popc(ba) + __popc(bb & lt)] = make_int2(kb1, (int)(cellg | 0u));
+                    }
+                    continue;
+                }
                 if ((int)lo == hi) {                  // one key in the whole cell: a single reduction
                     const int total = __reduce_add_sync(FULL, (a >= 0) + (b >= 0));
                     if (lane == 0) {
@@ -457,6 +554,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
                 }
             }
         }
+    }
+
+    if (P.mode == FZ_MODE_MARK || P.mode == FZ_MODE_EMIT) {   // bucketing passes end here; the step counter does not move
+        __syncthreads();
+        if (tid == 0) P.cta_tab[(P.mode == FZ_MODE_MARK ? 0 : gridDim.x) + blockIdx.x] = (int)*s_fill;
+        return;
     }
 
     // ------------------------------------------------------------------------------------------------- barrier 0
@@ -679,8 +782,10 @@ bool srx_fused_applicable(const srx_plan *p) {
     return true;
 }
 
+static int fz_grid(const srx_plan *p) { return p->fused_grid > 0 ? p->fused_grid : srx_sm_count_cached(); }
+
 template <typename IdT, typename XT>
-static int launch_fused_t(srx_plan *p, const srx_step_args *a, cudaStream_t st) {
+static int launch_fused_t(srx_plan *p, const srx_step_args *a, cudaStream_t st, int mode) {
     typedef FzLayout<IdT> L;
     const srx_plan_desc &d = p->d;
     auto kern = k_overlap_fused<IdT, XT>;
@@ -719,6 +824,10 @@ static int launch_fused_t(srx_plan *p, const srx_step_args *a, cudaStream_t st) 
     P.world = p->world;
     P.rank = p->world > 1 ? p->rank : 0;
     P.accum_vec = (int)(p->accum_bytes / 16);
+    P.mode = mode;
+    P.need = reinterpret_cast<unsigned char *>(p->ws + p->need_off);
+    P.cta_tab = reinterpret_cast<int *>(p->ws + p->ctatab_off);
+    P.pool = reinterpret_cast<int2 *>(p->pool);
     {
         static int dbg = -1;
         if (dbg < 0) { const char *e = getenv("SRX_FZ_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -727,7 +836,7 @@ static int launch_fused_t(srx_plan *p, const srx_step_args *a, cudaStream_t st) 
 
     cudaLaunchConfig_t cfg = {};
     // one CTA per SM on every rank (barrier targets rely on equal grids)
-    cfg.gridDim = dim3((unsigned)(p->fused_grid > 0 ? p->fused_grid : srx_sm_count_cached()));
+    cfg.gridDim = dim3((unsigned)fz_grid(p));
     cfg.blockDim = dim3(FZ_THREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = st;
@@ -743,18 +852,89 @@ static int launch_fused_t(srx_plan *p, const srx_step_args *a, cudaStream_t st) 
 }
 
 template <typename IdT>
-static int launch_fused_x(srx_plan *p, const srx_step_args *a, cudaStream_t st) {
+static int launch_fused_x(srx_plan *p, const srx_step_args *a, cudaStream_t st, int mode) {
     switch (a->x_dtype) {
-        case SRX_F32: return launch_fused_t<IdT, float>(p, a, st);
-        case SRX_F16: return launch_fused_t<IdT, __half>(p, a, st);
-        default: return launch_fused_t<IdT, __nv_bfloat16>(p, a, st);
+        case SRX_F32: return launch_fused_t<IdT, float>(p, a, st, mode);
+        case SRX_F16: return launch_fused_t<IdT, __half>(p, a, st, mode);
+        default: return launch_fused_t<IdT, __nv_bfloat16>(p, a, st, mode);
     }
 }
 
 int srx_launch_fused(srx_plan *p, const srx_step_args *a, cudaStream_t st) {
     SRX_REQUIRE((reinterpret_cast<uintptr_t>(a->ids_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->x_dev) & 15) == 0,
                 SRX_ERR_INVALID, "id buffers and latents must be 16-byte aligned");
-    return p->d.id_dtype == SRX_I32 ? launch_fused_x<int4>(p, a, st) : launch_fused_x<short4>(p, a, st);
+    int mode = FZ_MODE_STEP;
+    if (!a->ids_dev) {
+        SRX_REQUIRE(p->cache_ready && p->cache_grid == fz_grid(p), SRX_ERR_INVALID,
+                    "no ids given and no cached plan: call srx_plan_build_cache first (or pass ids_dev)");
+        mode = FZ_MODE_CACHED;
+    }
+    return p->d.id_dtype == SRX_I32 ? launch_fused_x<int4>(p, a, st, mode) : launch_fused_x<short4>(p, a, st, mode);
+}
+
+// Bucketing pass (SURVEY.md §8a K4-K5 for the cached-plan regime).  Two calls:
+//   1. pool_dev == NULL: streams the ids once (MARK): per-cell winners, bitmap of winner keys, pairs per CTA; syncs and
+//      lays the per-CTA regions out; *pool_bytes receives the size the caller must allocate.
+//   2. pool_dev != NULL: streams the ids again (EMIT) and fills the pool with the (key, cell, multiplicity) pairs whose
+//      key wins at least one cell.  Afterwards srx_overlap_step with ids_dev == NULL runs from the pool.
+extern "C" int srx_plan_build_cache(srx_plan *p, const void *ids_dev, void *pool_dev, int64_t *pool_bytes, void *stream) {
+    SRX_REQUIRE(p && p->ws && ids_dev && pool_bytes, SRX_ERR_INVALID, "null argument");
+    SRX_REQUIRE(p->fused, SRX_ERR_UNSUPPORTED, "the cached plan needs the persistent step kernel (8x8 pixels per cell, 4 channels, float accumulators)");
+    SRX_REQUIRE((long long)p->d.batch * p->d.lat_h * p->d.lat_w < (1ll << 26), SRX_ERR_UNSUPPORTED, "more than 2^26 latent cells");
+    SRX_REQUIRE((reinterpret_cast<uintptr_t>(ids_dev) & 15) == 0, SRX_ERR_INVALID, "id buffers must be 16-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int G = fz_grid(p);
+    int *tab = reinterpret_cast<int *>(p->ws + p->ctatab_off);
+    srx_step_args a;
+    memset(&a, 0, sizeof(a));
+    a.ids_dev = ids_dev;
+    a.x_dev = nullptr;
+    a.x_dtype = SRX_F32;
+    if (!pool_dev) {
+        p->cache_ready = false;
+        SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->need_off, 0, (size_t)p->kcap, st));
+        int rc = p->d.id_dtype == SRX_I32 ? launch_fused_x<int4>(p, &a, st, FZ_MODE_MARK) : launch_fused_x<short4>(p, &a, st, FZ_MODE_MARK);
+        if (rc) return rc;
+        std::vector<int> host(3 * (size_t)G, 0);
+        SRX_CUDA_CHECK(cudaMemcpyAsync(host.data(), tab, sizeof(int) * G, cudaMemcpyDeviceToHost, st));
+        SRX_CUDA_CHECK(cudaStreamSynchronize(st));
+        long long total = 0;
+        for (int b = 0; b < G; ++b) {
+            host[2 * G + b] = (int)total;
+            total += host[b];
+            SRX_REQUIRE(total < (1ll << 31), SRX_ERR_UNSUPPORTED, "more than 2^31 cached pairs");
+        }
+        SRX_CUDA_CHECK(cudaMemcpyAsync(tab + 2 * G, host.data() + 2 * G, sizeof(int) * G, cudaMemcpyHostToDevice, st));
+        SRX_CUDA_CHECK(cudaStreamSynchronize(st));   // host vector goes out of scope
+        p->cache_entries_cap = total;
+        p->cache_grid = G;
+        *pool_bytes = (total > 0 ? total : 1) * 8;
+        return SRX_OK;
+    }
+    SRX_REQUIRE(p->cache_grid == G && p->cache_entries_cap >= 0, SRX_ERR_INVALID, "call with pool_dev == NULL first");
+    SRX_REQUIRE(*pool_bytes >= (p->cache_entries_cap > 0 ? p->cache_entries_cap : 1) * 8, SRX_ERR_INVALID, "pool too small");
+    SRX_REQUIRE((reinterpret_cast<uintptr_t>(pool_dev) & 15) == 0, SRX_ERR_INVALID, "pool must be 16-byte aligned");
+    p->pool = pool_dev;
+    int rc = p->d.id_dtype == SRX_I32 ? launch_fused_x<int4>(p, &a, st, FZ_MODE_EMIT) : launch_fused_x<short4>(p, &a, st, FZ_MODE_EMIT);
+    if (rc) return rc;
+    p->cache_ready = true;
+    return SRX_OK;
+}
+
+// entries actually kept by the last srx_plan_build_cache (syncs); profiling / tests
+extern "C" int srx_plan_cache_entries(srx_plan *p, int64_t *kept, int64_t *capacity, void *stream) {
+    SRX_REQUIRE(p && p->ws && kept && capacity, SRX_ERR_INVALID, "null argument");
+    SRX_REQUIRE(p->cache_ready, SRX_ERR_INVALID, "no cached plan");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int G = p->cache_grid;
+    std::vector<int> host((size_t)G, 0);
+    SRX_CUDA_CHECK(cudaMemcpyAsync(host.data(), reinterpret_cast<int *>(p->ws + p->ctatab_off) + G, sizeof(int) * G, cudaMemcpyDeviceToHost, st));
+    SRX_CUDA_CHECK(cudaStreamSynchronize(st));
+    long long t = 0;
+    for (int b = 0; b < G; ++b) t += host[b];
+    *kept = t;
+    *capacity = p->cache_entries_cap;
+    return SRX_OK;
 }
 
 // Frame-sharded peer mode: `peer_ws[i]` is rank i's workspace as mapped into this process (CUDA IPC or symmetric
@@ -779,6 +959,7 @@ extern "C" int srx_plan_set_grid(srx_plan *p, int ctas) {
     SRX_REQUIRE(p, SRX_ERR_INVALID, "null plan");
     SRX_REQUIRE(ctas >= 0 && ctas <= srx_sm_count_cached(), SRX_ERR_INVALID, "grid must be between 0 and the SM count");
     p->fused_grid = ctas;
+    p->cache_ready = false;   // the cached plan is laid out per CTA
     return SRX_OK;
 }
 

@@ -586,6 +586,7 @@ extern "C" int srx_plan_get_info(const srx_plan *p, srx_plan_info *info) {
     info->accum_dtype = p->d.accum_mode == SRX_ACCUM_DETERMINISTIC ? -64 : SRX_F32;
     info->fast_path = p->fast_r8 ? 1 : 0;
     info->fused = p->fused ? 1 : 0;
+    info->need_offset = p->need_off;
     return SRX_OK;
 }
 
@@ -743,7 +744,6 @@ extern "C" int srx_overlap_step(srx_plan *p, const srx_step_args *a, void *strea
     if (p && a && p->fused) {
         int rc0 = check_step(p, a);
         if (rc0) return rc0;
-        SRX_REQUIRE(a->ids_dev, SRX_ERR_INVALID, "pass ids_dev");
         return srx_launch_fused(p, a, reinterpret_cast<cudaStream_t>(stream));
     }
     SRX_REQUIRE(p && p->world == 1, SRX_ERR_UNSUPPORTED, "peer mode is only available with the persistent step kernel");

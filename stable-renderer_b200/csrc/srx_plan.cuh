@@ -23,6 +23,11 @@ struct srx_plan {
     int world = 1, rank = 0;
     char *peers[SRX_MAX_PEERS] = {nullptr};
     int fused_grid = 0;   // CTAs of the persistent kernel; 0 = one per SM
+    // cached plan (srx_plan_build_cache)
+    int64_t need_off = 0, ctatab_off = 0, cache_entries_cap = -1;
+    void *pool = nullptr;
+    int cache_grid = 0;
+    bool cache_ready = false;
     bool fused = false;   // the persistent single-kernel step applies (fast_r8, float accumulators, aligned rows)
 };
 
@@ -62,6 +67,10 @@ static inline void plan_layout(srx_plan *p) {
                          // then [batch] u32 per-frame arrival counters (monotonic)
     p->stats_bytes = (int64_t)2 * d.batch * 16 * 8 + (int64_t)d.batch * 4;
     off = align_up(off + p->stats_bytes, 256);
+    p->need_off = off;   // [K] byte map of winner keys (cached plan); bytes so that ranks can combine theirs with a MAX all-reduce
+    off = align_up(off + p->kcap, 256);
+    p->ctatab_off = off; // [3][<= 1024 CTAs] per-CTA pair counts / kept entries / region starts (cached plan)
+    off += 3 * 1024 * 4;
     p->total_bytes = off;
 }
 

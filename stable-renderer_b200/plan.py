@@ -179,8 +179,58 @@ class OverlapPlan:
         a.cache_slots = 0
         return a
 
-    def step(self, x: torch.Tensor, ratio: float, *, adain: bool = True, ids: Optional[torch.Tensor] = None) -> None:
-        """One overlap step in place on x (reduce + gather on this GPU)."""
+    def build_cache(self, ids: Optional[torch.Tensor] = None) -> None:
+        """Bucketing pass (cached-plan regime): two streaming passes over the ids store, per CTA, the (key, cell,
+        multiplicity) pairs of the keys that win a cell; later `step(..., cached=True)` calls run from that pool without
+        touching the ids — the regime of denoise steps 2..N of one sampling run.  Syncs once (pool sizing)."""
+        ids = self._ids if ids is None else ids
+        if ids is None:
+            raise ValueError("this plan was built without ids: pass them")
+        if (tuple(ids.shape) != self.id_shape or ids.dtype != self.id_dtype or ids.device != self.device
+                or not ids.is_contiguous()):
+            raise ValueError("id buffers do not match the plan (shape / dtype / device / contiguity)")
+        self.cache_mark(ids)
+        if self.world > 1 and self.group is not None:
+            # a key matters if it wins a cell on ANY rank: its mean needs every rank's contributions
+            import torch.distributed as dist
+            dist.all_reduce(self.need_map, op=dist.ReduceOp.MAX, group=self.group)
+        self.cache_emit(ids)
+
+    @property
+    def need_map(self) -> torch.Tensor:
+        """[key_capacity] uint8: 1 where the key wins a cell (valid after cache_mark)."""
+        o = int(self.info.need_offset)
+        return self.workspace[o:o + self.key_capacity]
+
+    def cache_mark(self, ids: torch.Tensor) -> None:
+        lib = _lib.load()
+        nbytes = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.srx_plan_build_cache(self._handle, ids.data_ptr(), None, C.byref(nbytes), _lib.current_stream_ptr(self.device)))
+            self._pool = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.device)
+
+    def cache_emit(self, ids: torch.Tensor) -> None:
+        nbytes = C.c_int64(self._pool.numel())
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().srx_plan_build_cache(self._handle, ids.data_ptr(), self._pool.data_ptr(), C.byref(nbytes),
+                                                        _lib.current_stream_ptr(self.device)))
+        self.cached = True
+
+    def cache_entries(self) -> tuple:
+        kept, cap = C.c_int64(0), C.c_int64(0)
+        _lib.check(_lib.load().srx_plan_cache_entries(self._handle, C.byref(kept), C.byref(cap), _lib.current_stream_ptr(self.device)))
+        return int(kept.value), int(cap.value)
+
+    def step(self, x: torch.Tensor, ratio: float, *, adain: bool = True, ids: Optional[torch.Tensor] = None,
+             cached: bool = False) -> None:
+        """One overlap step in place on x (reduce + gather on this GPU; with a peer group also the exchange).
+        cached=True runs from the pool of `build_cache` instead of streaming the ids."""
+        if cached:
+            if not getattr(self, "cached", False):
+                raise _lib.SrxError("step(cached=True) needs build_cache() first")
+            a = self._args(x, None, ratio, adain, need_ids=False)
+            _lib.check(_lib.load().srx_overlap_step(self._handle, C.byref(a), _lib.current_stream_ptr(self.device)))
+            return
         a = self._args(x, ids, ratio, adain)
         _lib.check(_lib.load().srx_overlap_step(self._handle, C.byref(a), _lib.current_stream_ptr(self.device)))
 

@@ -172,3 +172,102 @@ def test_fused_large_vertex_ids_round_like_float32():
     pf.check()
     assert_close(t2n(a), want, RTOL, ATOL, "fused, ids around 2^24")
     assert_close(t2n(b), want, RTOL, ATOL, "split, ids around 2^24")
+
+
+@pytest.mark.parametrize("id_dtype", [torch.int32, torch.int16])
+def test_cached_plan_steps_match_oracle(id_dtype):
+    """Cached-plan regime: one bucketing pass over the ids, then several steps that never touch the ids again."""
+    from stable_renderer_b200.plan import OverlapPlan
+    ids, x0 = _inputs(5, 320, 320, 128, seed=41, id_dtype=id_dtype)
+    want = x0.numpy()
+    for _ in range(3):
+        want = O.overlap_step(want, ids.numpy(), None, ratio=0.5, accumulate="f64")
+    x = x0.cuda()
+    plan = OverlapPlan(ids.cuda(), x.shape, key_capacity=128 * 128)
+    plan.build_cache()
+    kept, cap = plan.cache_entries()
+    assert 0 < kept <= cap                      # only pairs whose key wins a cell are kept
+    n_valid = int(((ids[..., 2] != 2048) & (ids.abs().sum(-1) != 0)).sum())
+    assert cap <= n_valid                       # reduce-by-key inside the cell never produces more pairs than entries
+    for _ in range(3):
+        plan.step(x, 0.5, cached=True)
+    plan.check()
+    assert_close(t2n(x), want, 3e-5, 1e-5, f"3 cached steps {id_dtype}")
+    # a streaming step after cached steps keeps working on the same plan (shared accumulators / step counter)
+    want4 = O.overlap_step(want, ids.numpy(), None, ratio=0.5, accumulate="f64")
+    plan.step(x, 0.5)
+    assert_close(t2n(x), want4, 4e-5, 1e-5, "streaming step after cached steps")
+
+
+def test_cached_plan_requires_build():
+    from stable_renderer_b200 import _lib
+    from stable_renderer_b200.plan import OverlapPlan
+    ids, x0 = _inputs(2, 128, 128, 128, seed=3)
+    x = x0.cuda()
+    plan = OverlapPlan(ids.cuda(), x.shape, key_capacity=128 * 128)
+    with pytest.raises(_lib.SrxError):
+        plan.step(x, 0.5, cached=True)
+
+
+def test_corresponder_switches_to_cached_plan():
+    """The sampler-loop drop-in buckets the ids once it knows more steps follow (SamplingCallbackContext.total_steps)."""
+    from helpers import Ctx, EngineData
+    from stable_renderer_b200.corresponder import OverlapCorresponder
+    from stable_renderer_b200.corrmap import IDMap
+    ids, x0 = _inputs(4, 256, 256, 128, seed=9)
+    want = x0.numpy()
+    for _ in range(4):
+        want = O.overlap_step(want, ids.numpy(), None, ratio=0.3, accumulate="f64")
+    x = x0.cuda()
+    idm = IDMap(tensor=ids.cuda())
+    oc = OverlapCorresponder(step_finished_inject_ratio=0.3)
+    for i in range(4):
+        oc.step_finished(EngineData(idm), Ctx(x, 900.0, step_index=i, total_steps=20))
+    plan = next(iter(idm._plans.values()))
+    assert plan.fused and plan.cached
+    assert_close(t2n(x), want, 4e-5, 1e-5, "4 steps through the corresponder (cached plan)")
+    # without a step count the first call streams and the second one buckets
+    x2 = x0.cuda()
+    idm2 = IDMap(tensor=ids.cuda())
+
+    class Bare:
+        noise, timestep = x2, 900.0
+    oc.step_finished(EngineData(idm2), Bare())
+    p2 = next(iter(idm2._plans.values()))
+    assert not getattr(p2, "cached", False)
+    oc.step_finished(EngineData(idm2), Bare())
+    assert p2.cached
+
+
+def test_cached_plan_peer_exchange_two_ranks_on_one_gpu():
+    from stable_renderer_b200 import _lib
+    from stable_renderer_b200.plan import OverlapPlan
+    sms = _lib.load().srx_device_sm_count()
+    F, H = 8, 256
+    ids, x0 = _inputs(F, H, H, 256, seed=78)
+    ids = ids.cuda()
+    ref = x0.cuda()
+    cap = 256 * 256
+    pref = OverlapPlan(ids, ref.shape, key_capacity=cap)
+    xs = [x0[r * F // 2:(r + 1) * F // 2].contiguous().cuda() for r in range(2)]
+    plans = [OverlapPlan(ids[r * F // 2:(r + 1) * F // 2].contiguous(), xs[r].shape, key_capacity=cap) for r in range(2)]
+    ptrs = [p.workspace.data_ptr() for p in plans]
+    for r, p in enumerate(plans):
+        p.set_grid(sms // 2)
+        p.bind_peers(r, ptrs)
+        p.cache_mark(p._ids)
+    union = plans[0].need_map | plans[1].need_map      # what the MAX all-reduce does in a real frame-sharded run
+    for p in plans:
+        p.need_map.copy_(union)
+        p.cache_emit(p._ids)
+        p.cached = True
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for step in range(2):
+        pref.step(ref, 0.5)
+        torch.cuda.synchronize()
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                plans[r].step(xs[r], 0.5, cached=True)
+        torch.cuda.synchronize()
+        assert_close(t2n(torch.cat(xs, dim=0)), t2n(ref), 2e-5, 5e-6, f"cached + peer exchange, step {step}")
