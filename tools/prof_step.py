@@ -1,4 +1,5 @@
-"""Runs a few eager overlap steps (no CUDA graph) for ncu / compute-sanitizer: python tools/prof_step.py cfg2 [steps]"""
+"""Runs a few eager overlap steps (no CUDA graph) for ncu / compute-sanitizer: python tools/prof_step.py cfg2 [steps]
+SRX_PROF_CACHED=1 runs the bucketing pass + cached-plan steps instead of streaming steps."""
 import os
 import sys
 
@@ -20,8 +21,13 @@ ids = synthetic.make_ids(frames, H, H, tex_h=tex, tex_w=tex, n_obj=n_obj, frac_2
 ids2 = torch.roll(ids, 1, 0).contiguous()
 x = synthetic.make_latents(frames, 4, h, h, seed=0, dtype=dtype).to(dev)
 plan = OverlapPlan(None, x.shape, id_shape=ids.shape, id_dtype=ids.dtype, key_capacity=tex * tex, device=dev)
-for i in range(steps):
-    plan.step(x, RATIO, ids=ids if i % 2 == 0 else ids2)
+if os.environ.get("SRX_PROF_CACHED"):
+    plan.build_cache(ids)
+    for i in range(steps):
+        plan.step(x, RATIO, cached=True)
+else:
+    for i in range(steps):
+        plan.step(x, RATIO, ids=ids if i % 2 == 0 else ids2)
 torch.cuda.synchronize()
 plan.check()
 print("ok", wl, frames, float(x.float().abs().mean()))
