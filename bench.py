@@ -166,9 +166,9 @@ def barrier(world: int):
 def shard(frames_total: int, scaling: str, rank: int, world: int):
     if scaling == "weak":
         return frames_total, rank * frames_total, frames_total * world
-    assert frames_total % world == 0, f"{frames_total} frames do not split over {world} ranks"
-    per = frames_total // world
-    return per, rank * per, frames_total
+    from stable_renderer_b200.sharding import frame_shard
+    first, count = frame_shard(frames_total, rank, world)
+    return count, first, frames_total
 
 
 def run_overlap(args, rank: int, local: int, world: int) -> dict:
