@@ -30,7 +30,7 @@
 #define FZ_CPW (FZ_CELLS / FZ_CONS)       // cells per consumer warp per stage
 #define FZ_STAGES 6
 #define FZ_SLOT_BITS 25
-#define FZ_BU 2                           // cells per thread per round of the gather phase
+#define FZ_BU 4                           // cells per thread per round of the gather phase
 
 enum { FZ_ST_KEY_RANGE = 0 };
 // What the kernel does with the ids:
@@ -77,10 +77,12 @@ struct FzParams {
     int adain;
     int world, rank;
     int accum_vec;            // float4 vectors in one accumulator (sums then counts)
+    double inv_n, inv_nm1;    // 1 / (h*w), 1 / (h*w - 1)
     int mode;                 // FZ_MODE_*
     unsigned char *need;      // [kcap] 1 = the key wins some cell on some rank (the only keys whose mean is ever read)
     int *cta_tab;             // [3][gridDim]: pairs seen by each CTA (MARK), entries kept (EMIT), first entry of its region
     int2 *pool;               // cached plan: (slot, cell << 6 | multiplicity - 1) entries, one region per CTA
+    float *cnt_plan;          // cached plan: [kcap] entries per key on this rank (filled by EMIT; counts depend on the ids only)
     int dbg;                  // SRX_FZ_DEBUG experiment bits (results are wrong when set): 1 = no reductions,
                               // 2 = consumers only drain the ring, 4 = stop after phase A
 };
@@ -88,6 +90,9 @@ struct FzParams {
 // ---------------------------------------------------------------------------------------------------------------
 // PTX helpers
 // ---------------------------------------------------------------------------------------------------------------
+// release/acquire fence at GPU scope (MEMBAR.ALL.GPU).  __threadfence() is the sequentially-consistent fence.sc.gpu,
+// which is measurably slower and stronger than anything the counters below need.
+__device__ __forceinline__ void fz_fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
@@ -213,7 +218,7 @@ __device__ __forceinline__ FzRec fz_rec_wait(const char *p, unsigned flag) {
 // Grid-wide (and, with peers, box-wide) barrier `b`: every CTA adds 1 to counter [b][my rank] on each participant and
 // waits until each of its own counters [b][p] has reached target = step * gridDim.x.  All ranks launch the same grid.
 __device__ __forceinline__ void fz_barrier(const FzParams &P, int b, unsigned target, bool cross) {
-    __threadfence();
+    fz_fence_gpu();
     __syncthreads();
     const int nsrc = cross ? P.world : 1;
     const bool sys = cross && P.world > 1;
@@ -227,7 +232,8 @@ __device__ __forceinline__ void fz_barrier(const FzParams &P, int b, unsigned ta
         const int src = cross ? (int)threadIdx.x : P.rank;
         const unsigned *mine = reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + b * SRX_MAX_PEERS + src;
         while ((int)(ld_relaxed(mine, sys) - target) < 0) { }
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        // no acquire fence: everything read after this barrier that another SM (or GPU) wrote is loaded past L1
+        // (ld.cg / ld.relaxed.sys); the fence would only add an L1 invalidation and ~0.7 us
     }
     __syncthreads();
 }
@@ -263,6 +269,50 @@ __device__ __forceinline__ double fz_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Sums 16 per-lane values over the warp with 16 shuffles instead of 80: every butterfly stage halves the number of
+// values a lane still carries (the lane keeps the half selected by its own bit and hands the other half to its partner).
+// On return lane L (L < 16) holds in s[0] the warp-wide sum of value index L's ... see mapping below: index = bit-reversal
+// free layout: after stages xor 16, 8, 4, 2 a lane holds value j = (lane >> 1) & 15 ... we only need: lane 2*j holds sum j.
+__device__ __forceinline__ double fz_warp_sum16(double (&s)[16], int lane) {
+    const unsigned FULL = 0xffffffffu;
+    // stage xor 16: 16 -> 8 values; lanes with bit 4 set keep the upper half
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double give = up ? s[j] : s[j + 8];
+            const double keep = up ? s[j + 8] : s[j];
+            s[j] = keep + __shfl_xor_sync(FULL, give, 16);
+        }
+    }
+    {   // xor 8: 8 -> 4
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double give = up ? s[j] : s[j + 4];
+            const double keep = up ? s[j + 4] : s[j];
+            s[j] = keep + __shfl_xor_sync(FULL, give, 8);
+        }
+    }
+    {   // xor 4: 4 -> 2
+        const bool up = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double give = up ? s[j] : s[j + 2];
+            const double keep = up ? s[j + 2] : s[j];
+            s[j] = keep + __shfl_xor_sync(FULL, give, 4);
+        }
+    }
+    {   // xor 2: 2 -> 1
+        const bool up = lane & 2;
+        const double give = up ? s[0] : s[1];
+        const double keep = up ? s[1] : s[0];
+        s[0] = keep + __shfl_xor_sync(FULL, give, 2);
+    }
+    // xor 1: both lanes of a pair end with the full sum of value index ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1)
+    return s[0] + __shfl_xor_sync(FULL, s[0], 1);
 }
 
 // Exchange, owner side: pull the partial sums of this rank's slots from every peer, add in rank order, keep the totals
@@ -377,6 +427,13 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             float4 *st_other = reinterpret_cast<float4 *>(P.ws + P.stats_off + (long long)(par ^ 1) * P.batch * 128);
             for (int v = blockIdx.x * FZ_CONS * 32 + tid; v < P.batch * 8; v += stride) st_other[v] = z;
         }
+        // the counts depend on the ids only: copy them from the plan instead of reducing them again (the count region
+        // of this step's accumulator was cleared during the previous step and nothing else writes it in this mode)
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(P.cnt_plan);
+            float4 *dst = reinterpret_cast<float4 *>(cnt);
+            for (int v = blockIdx.x * FZ_THREADS + tid; v < (int)(P.kcap / 4); v += gridDim.x * FZ_THREADS) dst[v] = __ldg(src + v);
+        }
         const int G = gridDim.x;
         const int e0 = P.cta_tab[2 * G + blockIdx.x], e1 = e0 + P.cta_tab[G + blockIdx.x];
         const XT *xs = reinterpret_cast<const XT *>(P.x);
@@ -389,7 +446,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             const XT *xp = xs + (long long)fr * 4 * n + ci;
             const float x0 = XIo<XT>::ld(xp), x1 = XIo<XT>::ld(xp + n), x2 = XIo<XT>::ld(xp + 2 * n), x3 = XIo<XT>::ld(xp + 3 * n);
             red_add_f32x4(acc + (long long)en.x * 4, fm * x0, fm * x1, fm * x2, fm * x3);
-            red_add_f32(cnt + en.x, fm);
         }
     } else if (warp == FZ_CONS) {
         // producer.  Items (8 id rows x 32 cells) are dealt round-robin in CHUNK-MAJOR order (all rows of column chunk
@@ -525,8 +581,14 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
                         const unsigned lt = (1u << lane) - 1u;
                         const unsigned cellg = (unsigned)(desc.x + cell) << 6;
                         int2 *dst = P.pool + P.cta_tab[2 * gridDim.x + blockIdx.x] + base;
-                        if (fa) dst[__popc(ba & lt)] = make_int2(ka1, (int)(cellg | (unsigned)(ma - 1)));
-                        if (fb) dst[__popc(ba) + __popc(bb & lt)] = make_int2(kb1, (int)(cellg | 0u));
+                        if (fa) {
+                            dst[__popc(ba & lt)] = make_int2(ka1, (int)(cellg | (unsigned)(ma - 1)));
+                            red_add_f32(P.cnt_plan + ka1, (float)ma);
+                        }
+                        if (fb) {
+                            dst[__popc(ba) + __popc(bb & lt)] = make_int2(kb1, (int)(cellg | 0u));
+                            red_add_f32(P.cnt_plan + kb1, 1.f);
+                        }
                     }
                     continue;
                 }
@@ -600,7 +662,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         FZ_TRACE(3);
         // Tell every peer that this CTA (a) has stored its share of this rank's total records — the fence puts them in
         // this GPU's L2 first — and (b) no longer reads the peer's accumulator of this step (peers clear it two steps on).
-        __threadfence();
+        fz_fence_gpu();
         __syncthreads();
         if (tid < P.world)
             red_relaxed_add(reinterpret_cast<unsigned *>(P.peers[tid] + P.pads_off) + 1 * SRX_MAX_PEERS + P.rank, 1u);
@@ -618,8 +680,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
 
     // ------------------------------------------------------------------------------------------------- phases B, C
     // Each latent frame is handled by a group of `grp` CTAs (grp = gridDim / frames when there are fewer frames than
-    // CTAs, else 1 and a CTA walks over several frames).  Only the CTAs of one frame exchange statistics, through
-    // that frame's own arrival counter, so no grid-wide barrier separates gather and AdaIN.
+    // CTAs — measured: 1024 cells per CTA beat 4096 by 4 us on cfg2 — else 1 and a CTA walks over several frames).
+    // Only the CTAs of one frame exchange statistics, through that frame's own arrival counter, so no grid-wide barrier
+    // separates gather and AdaIN.  The latents read for the gather stay in shared memory (the ring is idle by now) for
+    // the AdaIN pass.
     XT *x = reinterpret_cast<XT *>(P.x);
     double *red = reinterpret_cast<double *>(smem + L::RED_OFF);
     float *coef = reinterpret_cast<float *>(smem + L::COEF_OFF);
@@ -627,6 +691,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
     unsigned *fcount = reinterpret_cast<unsigned *>(P.ws + P.stats_off + (long long)2 * P.batch * 128);
     const int G = gridDim.x;
     const int grp = P.batch >= G ? 1 : G / P.batch;
+    float4 *sx4 = reinterpret_cast<float4 *>(smem);                       // [cells of this CTA] staged latents
+    const int smem_cells = (int)(FZ_STAGES * L::STAGE / 16);
     const int f_first = grp == 1 ? (int)blockIdx.x : (int)blockIdx.x / grp;
     const int f_step = grp == 1 ? G : P.batch;          // grouped CTAs handle exactly one frame
     const int part = grp == 1 ? 0 : (int)blockIdx.x % grp;
@@ -634,6 +700,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         const int s0 = (int)((long long)n * part / grp), s1 = (int)((long long)n * (part + 1) / grp);
         XT *xf = x + (long long)f * 4 * n;
         const int *wf = P.winner + (long long)f * n;
+        const bool staged = (s1 - s0) <= smem_cells;
         double sums[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) sums[j] = 0.0;
@@ -654,6 +721,13 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
                 const int ci = min(c0 + u * FZ_THREADS, s1 - 1);
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) xv[u][ch] = XIo<XT>::ld(xf + (long long)ch * n + ci);
+            }
+            if (staged && P.adain) {
+#pragma unroll
+                for (int u = 0; u < FZ_BU; ++u) {
+                    const int ci = c0 + u * FZ_THREADS;
+                    if (ci < s1) sx4[ci - s0] = make_float4(xv[u][0], xv[u][1], xv[u][2], xv[u][3]);
+                }
             }
 #pragma unroll
             for (int u = 0; u < FZ_BU; ++u) {
@@ -698,10 +772,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             }
         }
         if (!P.adain) continue;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const double v = fz_warp_sum(sums[j]);
-            if (lane == 0) red[warp * 16 + j] = v;
+        FZ_TRACE(5);
+        {
+            const double v = fz_warp_sum16(sums, lane);
+            // lane pair (2q, 2q+1) holds value index j with bits: j3 = lane bit 4, j2 = bit 3, j1 = bit 2, j0 = bit 1
+            const int j = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if ((lane & 1) == 0) red[warp * 16 + j] = v;
         }
         __syncthreads();
         double *fs = stats + (long long)f * 16;
@@ -712,12 +788,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             else red[tid] = v;                         // warp 0 only reads rows written before the barrier above
         }
         if (grp > 1) {                                 // the frame's CTAs meet at the frame's own counter
-            __threadfence();
+            fz_fence_gpu();
             __syncthreads();
-            if (tid == 0) {
-                red_release_add(fcount + f, 1u, false);
+            if (tid == 0) {   // the fence above already ordered this CTA's sums: a relaxed arrival is enough
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(fcount + f), "r"(1u) : "memory");
                 const unsigned tgt = epoch * (unsigned)grp;
-                while ((int)(ld_acquire(fcount + f, false) - tgt) < 0) { }
+                while ((int)(ld_relaxed(fcount + f, false) - tgt) < 0) { }   // the sums are read with ld.cg below
             }
         }
         __syncthreads();
@@ -725,23 +801,30 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             double sx, sxx, sb, sbb;
             if (grp > 1) { sx = __ldcg(fs + tid * 4); sxx = __ldcg(fs + tid * 4 + 1); sb = __ldcg(fs + tid * 4 + 2); sbb = __ldcg(fs + tid * 4 + 3); }
             else { sx = red[tid * 4]; sxx = red[tid * 4 + 1]; sb = red[tid * 4 + 2]; sbb = red[tid * 4 + 3]; }
-            const double dn = (double)n;
-            // unbiased variance + 1e-5, sqrt (math_utils.py:39-47)
-            coef[tid * 4 + 0] = (float)(sx / dn);
-            coef[tid * 4 + 1] = __fsqrt_rn(__fadd_rn((float)((sxx - sx * sx / dn) / (dn - 1.0)), 1e-5f));
-            coef[tid * 4 + 2] = __fsqrt_rn(__fadd_rn((float)((sbb - sb * sb / dn) / (dn - 1.0)), 1e-5f));
-            coef[tid * 4 + 3] = (float)(sb / dn);
+            // unbiased variance + 1e-5, sqrt (math_utils.py:39-47); 1/n and 1/(n-1) come from the host in double
+            coef[tid * 4 + 0] = (float)(sx * P.inv_n);
+            coef[tid * 4 + 1] = __fsqrt_rn(__fadd_rn((float)((sxx - sx * sx * P.inv_n) * P.inv_nm1), 1e-5f));
+            coef[tid * 4 + 2] = __fsqrt_rn(__fadd_rn((float)((sbb - sb * sb * P.inv_n) * P.inv_nm1), 1e-5f));
+            coef[tid * 4 + 3] = (float)(sb * P.inv_n);
         }
         __syncthreads();
+        FZ_TRACE(6);
 #pragma unroll 4
         for (int ci = s0 + tid; ci < s1; ci += FZ_THREADS) {
+            float v[4];
+            if (staged) {
+                const float4 t = sx4[ci - s0];
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) v[ch] = XIo<XT>::ld(xf + (long long)ch * n + ci);
+            }
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
-                XT *p = xf + (long long)ch * n + ci;
-                const float v = XIo<XT>::ld(p);
                 // ((x - mu_c) / sigma_c) * sigma_s + mu_s : one rounding per op (math_utils.py:78-80)
-                XIo<XT>::st(p, __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(v, coef[ch * 4 + 0]), coef[ch * 4 + 1]), coef[ch * 4 + 2]),
-                                         coef[ch * 4 + 3]));
+                XIo<XT>::st(xf + (long long)ch * n + ci,
+                            __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(v[ch], coef[ch * 4 + 0]), coef[ch * 4 + 1]), coef[ch * 4 + 2]),
+                                      coef[ch * 4 + 3]));
             }
         }
         __syncthreads();
@@ -824,10 +907,13 @@ static int launch_fused_t(srx_plan *p, const srx_step_args *a, cudaStream_t st, 
     P.world = p->world;
     P.rank = p->world > 1 ? p->rank : 0;
     P.accum_vec = (int)(p->accum_bytes / 16);
+    P.inv_n = 1.0 / ((double)d.lat_h * d.lat_w);
+    P.inv_nm1 = 1.0 / ((double)d.lat_h * d.lat_w - 1.0);
     P.mode = mode;
     P.need = reinterpret_cast<unsigned char *>(p->ws + p->need_off);
     P.cta_tab = reinterpret_cast<int *>(p->ws + p->ctatab_off);
     P.pool = reinterpret_cast<int2 *>(p->pool);
+    P.cnt_plan = reinterpret_cast<float *>(p->ws + p->cntp_off);
     {
         static int dbg = -1;
         if (dbg < 0) { const char *e = getenv("SRX_FZ_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -915,6 +1001,7 @@ extern "C" int srx_plan_build_cache(srx_plan *p, const void *ids_dev, void *pool
     SRX_REQUIRE(*pool_bytes >= (p->cache_entries_cap > 0 ? p->cache_entries_cap : 1) * 8, SRX_ERR_INVALID, "pool too small");
     SRX_REQUIRE((reinterpret_cast<uintptr_t>(pool_dev) & 15) == 0, SRX_ERR_INVALID, "pool must be 16-byte aligned");
     p->pool = pool_dev;
+    SRX_CUDA_CHECK(cudaMemsetAsync(p->ws + p->cntp_off, 0, (size_t)p->kcap * 4, st));
     int rc = p->d.id_dtype == SRX_I32 ? launch_fused_x<int4>(p, &a, st, FZ_MODE_EMIT) : launch_fused_x<short4>(p, &a, st, FZ_MODE_EMIT);
     if (rc) return rc;
     p->cache_ready = true;
@@ -964,7 +1051,8 @@ extern "C" int srx_plan_set_grid(srx_plan *p, int ctas) {
 }
 
 // Phase timestamps of the last step (SM clock ticks relative to kernel entry): out[0..7] first CTA, out[8..15] last CTA.
-// Indices: 0 entry, 1 phase A done, 2 barrier 0 passed, 3 exchange done, 4 barrier 1 passed, 7 exit (5, 6 unused).  Syncs the stream.  Profiling aid.
+// Indices: 0 entry, 1 phase A done, 2 barrier 0 passed, 3 exchange done, 4 signal round done, 5 gather loop done,
+// 6 statistics reduced, 7 exit.  Syncs the stream.  Profiling aid.
 extern "C" int srx_plan_read_trace(srx_plan *p, int64_t *out16, void *stream) {
     SRX_REQUIRE(p && p->ws && out16, SRX_ERR_INVALID, "null argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -24,7 +24,7 @@ struct srx_plan {
     char *peers[SRX_MAX_PEERS] = {nullptr};
     int fused_grid = 0;   // CTAs of the persistent kernel; 0 = one per SM
     // cached plan (srx_plan_build_cache)
-    int64_t need_off = 0, ctatab_off = 0, cache_entries_cap = -1;
+    int64_t need_off = 0, ctatab_off = 0, cntp_off = 0, cache_entries_cap = -1;
     void *pool = nullptr;
     int cache_grid = 0;
     bool cache_ready = false;
@@ -69,6 +69,8 @@ static inline void plan_layout(srx_plan *p) {
     off = align_up(off + p->stats_bytes, 256);
     p->need_off = off;   // [K] byte map of winner keys (cached plan); bytes so that ranks can combine theirs with a MAX all-reduce
     off = align_up(off + p->kcap, 256);
+    p->cntp_off = off;   // [K] f32 entries per key of this rank's ids (cached plan)
+    off = align_up(off + (p->fused ? p->kcap * 4 : 0), 256);
     p->ctatab_off = off; // [3][<= 1024 CTAs] per-CTA pair counts / kept entries / region starts (cached plan)
     off += 3 * 1024 * 4;
     p->total_bytes = off;

@@ -29,8 +29,11 @@ ids.append(torch.roll(ids[0], 2, 0).contiguous())
 x = synthetic.make_latents(F, 4, h, h, seed=0, dtype=dtype).to(dev)
 plan = OverlapPlan(None, x.shape, id_shape=ids[0].shape, id_dtype=ids[0].dtype, key_capacity=tex * tex, device=dev,
                    process_group=dist.group.WORLD if (world > 1 and not os.environ.get("SRX_TRACE_NOPEER")) else None)
-names = ["A stream", "barrier0", "X pull+reduce", "signal", "B+C gather/adain"]
-acc = [[0.0] * 5 for _ in range(2)]
+CACHED = bool(os.environ.get("SRX_TRACE_CACHED"))
+if CACHED:
+    plan.build_cache(ids[0])
+names = ["A stream", "barrier0", "X pull+reduce", "signal", "B gather loop", "stats reduce", "C adain"]
+acc = [[0.0] * 7 for _ in range(2)]
 n = 30
 mhz = 1965.0
 ev_ms = 0.0
@@ -39,7 +42,7 @@ for i in range(n + 5):
     if world > 1:
         dist.barrier()
     e0.record()
-    plan.step(x, 0.5, ids=ids[i % 3])
+    plan.step(x, 0.5, ids=ids[i % 3], cached=CACHED)
     e1.record()
     torch.cuda.synchronize()
     if i >= 5:
@@ -50,8 +53,9 @@ for i in range(n + 5):
             t = tr[key]
             if world == 1:
                 t = t[:3] + [t[2], t[2]] + t[5:]      # no exchange phase: stamps 3, 4 are not written
-            t = t[:5] + [t[7]]
-            for j in range(5):
+            if t[5] < t[4] or t[6] < t[5]:
+                t = t[:5] + [t[7], t[7], t[7]]      # idle CTA in the gather phase
+            for j in range(7):
                 acc[w][j] += (t[j + 1] - t[j]) / mhz / n
 # back-to-back eager launches without host syncs in between
 torch.cuda.synchronize()
@@ -60,19 +64,18 @@ if world > 1:
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for i in range(60):
-    plan.step(x, 0.5, ids=ids[i % 3])
+    plan.step(x, 0.5, ids=ids[i % 3], cached=CACHED)
 e1.record()
 torch.cuda.synchronize()
 b2b = e0.elapsed_time(e1) / 60 * 1e3
 ring = [r for r in plan.read_step_ring() if r[1] > 0 and r[0] != (1 << 64) - 1]
 ring.sort()
 spans = [(e - s) / 1e3 for s, e, _ in ring]
-ss_parts = [0.0] * 5
+ss_parts = [0.0] * 7
 for _, _, st in ring[-16:]:
     if world == 1:
         st = st[:3] + [st[2], st[2]] + st[5:]
-    st = st[:5] + [st[7]]
-    for j in range(5):
+    for j in range(7):
         ss_parts[j] += (st[j + 1] - st[j]) / mhz / 16
 ss_txt = ", ".join(f"{nm} {v:.1f}" for nm, v in zip(names, ss_parts))
 gaps = [(ring[i + 1][0] - ring[i][1]) / 1e3 for i in range(len(ring) - 1)]
@@ -83,7 +86,7 @@ tr = plan.read_trace()["first_cta"]
 last_span = (tr[7] - tr[0]) / mhz
 if world == 1:
     tr = tr[:3] + [tr[2], tr[2]] + tr[5:]
-trl = tr[:5] + [tr[7]]
+trl = tr
 b2b_parts = ", ".join(f"{nm} {(trl[j + 1] - trl[j]) / mhz:.1f}" for j, nm in enumerate(names))
 if world > 1:
     dist.barrier()
