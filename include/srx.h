@@ -176,6 +176,40 @@ int srx_group_by_then_average(const float *values_dev, const float *keys_dev, in
                               float *out_dev, float *workspace_dev, int64_t key_capacity, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Same-key broadcast initialisers — replace tensor_group_by_then_randn_init (source/common_utils/math_utils.py:164-229)
+ * and the arithmetic of CreateNoiseSequenceFromIdMap (source/comfyUI/stable_rendering/_nodes/loaders.py:193-271).
+ * The reference's `unique(return_inverse=True)` sort becomes a dense presence table + exclusive scan; the random rows
+ * are still drawn by the caller with torch.randn (same call as the reference => same values on the same device).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* ints the rank table workspace must hold for a key capacity */
+int64_t srx_group_rank_workspace_ints(int64_t key_capacity);
+/* keys [n] float32 (non-negative integers < key_capacity).  On return table_ws[k] = rank of key k among the sorted unique
+ * keys or -1, rank_out[i] (optional) = rank of keys[i] = torch.unique's `inverse`, *n_unique = number of unique keys.  Syncs. */
+int srx_group_rank(const float *keys_dev, int64_t n, int64_t key_capacity, int32_t *table_ws, int32_t *rank_out,
+                   int64_t *n_unique, void *stream);
+/* the same table straight from id buffers: key = float32(vertexID) of every pixel kept by corrmap.py:266-275.  Syncs. */
+int srx_ids_rank_table(const void *ids_dev, int id_dtype, int frames, int height, int width, int64_t key_capacity,
+                       int32_t *table_ws, int64_t *n_unique, void *stream);
+/* out[i, :] = table[rank[i], :]  —  random_values[inverse_indices] (math_utils.py:224) */
+int srx_group_broadcast(const float *table_dev, const int32_t *rank_dev, int64_t n, int channels, float *out_dev, void *stream);
+
+typedef struct srx_noise_args {
+    const void *ids_dev;          /* [F,H,W,4]; H, W must equal the node's 512 / 1024 working size */
+    int id_dtype;
+    int frames, height, width;
+    const int32_t *inv_frame_dev; /* [F] id frame that writes latent frame f, or -1 (inverse of IDMap.frame_indices) */
+    const int32_t *rank_table_dev;/* from srx_ids_rank_table */
+    const float *key_latent_dev;  /* [n_unique,4] random row per key for the latent (mode 0 only) */
+    const float *key_noise_dev;   /* [n_unique,4] random row per key for the noise */
+    const float *base_latent_dev; /* [4,H,W] the node's base latent draw (mode 0 only) */
+    const float *base_noise_dev;  /* [4,H,W] */
+    float *latent_out_dev;        /* mode 0: [F,4,H/8,W/8] */
+    float *noise_out_dev;         /* mode 0: [F,4,H/8,W/8]; modes 1-3: F*4*H*W/32 floats (the node views them as [2F,4,H/8,W/8]) */
+    int mode;                     /* downsample_option: 0 nearest, 1 mean, 2 max, 3 min (loaders.py:252-268) */
+} srx_noise_args;
+int srx_noise_from_ids(const srx_noise_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Legacy overlap — replaces ResizeOverlap.__call__ / Overlap.__call__ with kernel_radius 0
  * (legacy_codes/stable_rendering_algo/overlap/overlap.py:83-152,180-222) for the four OverlapAlgorithm strategies
  * (overlap/algorithms.py:34-118).  Latents [T,B,C,h,w] (B folded into channels), ids [T,H,W,4] keyed by the whole id

@@ -209,12 +209,58 @@ def group_cases(R):
          b=b.numpy(), ub=ub.numpy(), content=c.numpy(), style=s.numpy(), adain=ad.numpy())
 
 
+def randn_init_cases(R):
+    """tensor_group_by_then_randn_init (math_utils.py:164-229) on the CPU generator, and the arithmetic of
+    CreateNoiseSequenceFromIdMap (_nodes/loaders.py:193-271).  The node class itself cannot be imported (it needs the
+    ComfyUI type system), so its body is replayed here step by step around the reference's REAL grouping function, on CPU."""
+    import torch.nn.functional as Fnn
+    mu = R["math_utils"]
+    g = torch.Generator().manual_seed(3)
+    t = torch.cat([torch.randn(4000, 3, generator=g), torch.randint(0, 500, (4000, 1), generator=g).float()], dim=1)
+    torch.manual_seed(11)
+    exp, uniq = mu.tensor_group_by_then_randn_init(t, index_column=-1, value_columns=[0, 1, 2], return_unique=True)
+    torch.manual_seed(11)
+    table = torch.randn(len(uniq), 3)
+    u2, inv = t[:, -1].unique(return_inverse=True)
+    assert torch.equal(u2, uniq) and torch.equal(exp, table[inv]), "randn_like(expanded unique) != randn(n_unique, C)"
+    save("randn_init", t=t.numpy(), expanded=exp.numpy(), unique=uniq.numpy(), inverse=inv.numpy().astype(np.int32),
+         table=table.numpy(), seed=np.int64(11))
+
+    from stable_renderer_b200 import synthetic
+    corrmap = R["corrmap"]
+    size, F, seed = 512, 1, 77
+    ids = synthetic.make_ids(F, size, size, tex_h=96, tex_w=96, frac_2048=0.05, seed=17)
+    out = {}
+    for option in ("nearest", "mean", "max", "min"):
+        idm = corrmap.IDMap(tensor=ids.clone())
+        latent_generator = torch.manual_seed(seed)
+        noise_generator = torch.manual_seed(seed + 1)
+        latent = torch.randn([1, 4, size, size], device="cpu", generator=latent_generator).repeat(F, 1, 1, 1)
+        noise = torch.randn([1, 4, size, size], device="cpu", generator=noise_generator).repeat(F, 1, 1, 1)
+        with ref_shim.quiet():
+            vsi = idm.create_vertex_screen_info()
+        xs, ys, fs = (vsi[:, 4] * size).long(), (vsi[:, 5] * size).long(), vsi[:, 6].long()
+        for tensor in (latent, noise):
+            tab = torch.cat([tensor[fs, :, ys, xs], vsi[:, 3].unsqueeze(-1)], dim=-1)
+            rnd, _ = mu.tensor_group_by_then_randn_init(tab, index_column=-1, value_columns=[0, 1, 2, 3], return_unique=True)
+            tensor[fs, :, ys, xs] = rnd
+        if option == "nearest":
+            out["nearest_samples"] = Fnn.interpolate(latent, size=(size // 8, size // 8), mode="nearest").numpy()
+            out["nearest_noise"] = Fnn.interpolate(noise, size=(size // 8, size // 8), mode="nearest").numpy()
+        else:
+            v = noise.view(-1, 4, 8, 8)
+            v = {"mean": lambda a: a.mean(dim=(1, 2)), "max": lambda a: a.amax(dim=(1, 2)), "min": lambda a: a.amin(dim=(1, 2))}[option](v)
+            out[option + "_noise"] = v.view(-1, 4, size // 8, size // 8).numpy()
+    save("noise_from_idmap", seed=np.int64(seed), id_seed=np.int64(17), tex=np.int64(96), size=np.int64(size), frames=np.int64(F), **out)
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit("reference tree not mounted; fixtures can only be regenerated in the build container")
     torch.set_num_threads(1)
     R = ref_shim.load_reference()
     group_cases(R)
+    randn_init_cases(R)
     step_cases(R)
     bake_cases(R)
     legacy_cases(R)

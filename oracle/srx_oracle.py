@@ -508,3 +508,48 @@ def group_slots(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     """(unique sorted keys, inverse) — the bucketing shared by average / randn_init."""
     uniq, inv = np.unique(np.asarray(keys), return_inverse=True)
     return uniq, inv.reshape(-1)
+
+
+def randn_init_expand(keys: np.ndarray, random_values: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """``tensor_group_by_then_randn_init`` given the random rows (math_utils.py:216-224): row i receives
+    ``random_values[inverse[i]]`` where inverse is the rank of ``keys[i]`` among the sorted unique keys."""
+    uniq, inv = group_slots(keys)
+    return np.asarray(random_values)[inv], uniq
+
+
+def noise_sequence_from_ids(ids: np.ndarray, frame_indices: Optional[Sequence[int]], base_latent: np.ndarray,
+                            base_noise: np.ndarray, key_latent: np.ndarray, key_noise: np.ndarray, size: int,
+                            downsample_option: str = "nearest"):
+    """``CreateNoiseSequenceFromIdMap.__call__`` given its four random draws (_nodes/loaders.py:193-271).
+
+    base_* [1,4,size,size] (the CPU draws, :212-219), key_* [n_unique,4] (one row per sorted unique vertex id, the draws
+    inside tensor_group_by_then_randn_init).  Steps: repeat the base per frame (:215,220); entries from
+    ``create_vertex_screen_info``; pixel = (trunc(x_ratio*size), trunc(y_ratio*size)), frame = column 6 (:224-226); the
+    entry's key row overwrites ``tensor[frame, :, y, x]`` — duplicate indices resolved last-entry-wins (:238-243,262-267);
+    then 'nearest' (F.interpolate to size/8 keeps pixel (8i, 8j), :269-272) or the [-1,4,8,8] view reduction over dims
+    (1,2), which runs over 256 CONSECUTIVE floats of a row and yields 2F frames (:274-285), samples = zeros there."""
+    F = ids.shape[0]
+    vsi = vertex_screen_info(ids, frame_indices)
+    sx = (vsi[:, 4] * np.float32(size)).astype(np.int64)
+    sy = (vsi[:, 5] * np.float32(size)).astype(np.int64)
+    fr = vsi[:, 6].astype(np.int64)
+    uniq, inv = group_slots(vsi[:, 3])
+    outs = []
+    for base, key in ((base_latent, key_latent), (base_noise, key_noise)):
+        full = np.repeat(np.asarray(base, dtype=np.float32), F, axis=0)           # [F,4,size,size]
+        flat = fr * (size * size) + sy * size + sx
+        last = np.full(F * size * size, -1, dtype=np.int64)
+        np.maximum.at(last, flat, np.arange(flat.size, dtype=np.int64))
+        hit = np.nonzero(last >= 0)[0]
+        vals = np.asarray(key, dtype=np.float32)[inv[last[hit]]]                  # [n_hit,4]
+        f_h, rem = hit // (size * size), hit % (size * size)
+        full[f_h, :, rem // size, rem % size] = vals
+        outs.append(full)
+    latent, noise = outs
+    h = size // 8
+    if downsample_option == "nearest":
+        return latent[:, :, ::8, ::8].copy(), noise[:, :, ::8, ::8].copy()
+    red = {"mean": lambda a: a.mean(axis=(1, 2), dtype=np.float32), "max": lambda a: a.max(axis=(1, 2)),
+           "min": lambda a: a.min(axis=(1, 2))}[downsample_option]
+    noise = red(noise.reshape(-1, 4, 8, 8)).reshape(-1, 4, h, h)
+    return np.zeros_like(noise), noise

@@ -57,6 +57,13 @@ class srx_legacy_args(C.Structure):
                 ("view_normal_dev", C.c_void_p), ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
+class srx_noise_args(C.Structure):
+    _fields_ = [("ids_dev", C.c_void_p), ("id_dtype", C.c_int), ("frames", C.c_int), ("height", C.c_int), ("width", C.c_int),
+                ("inv_frame_dev", C.c_void_p), ("rank_table_dev", C.c_void_p), ("key_latent_dev", C.c_void_p),
+                ("key_noise_dev", C.c_void_p), ("base_latent_dev", C.c_void_p), ("base_noise_dev", C.c_void_p),
+                ("latent_out_dev", C.c_void_p), ("noise_out_dev", C.c_void_p), ("mode", C.c_int)]
+
+
 class srx_bake_args(C.Structure):
     _fields_ = [("values_dev", C.c_void_p), ("writtens_dev", C.c_void_p), ("k2", C.c_int), ("texels", C.c_int),
                 ("channels", C.c_int), ("colors_dev", C.c_void_p), ("color_dtype", C.c_int), ("color_channels", C.c_int),
@@ -75,6 +82,12 @@ _PROTOTYPES = {
     "srx_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(srx_plan_info)]),
     "srx_plan_bind_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "srx_plan_bind_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "srx_group_rank_workspace_ints": (C.c_int64, [C.c_int64]),
+    "srx_group_rank": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "srx_ids_rank_table": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p,
+                                     C.POINTER(C.c_int64), C.c_void_p]),
+    "srx_group_broadcast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "srx_noise_from_ids": (C.c_int, [C.POINTER(srx_noise_args), C.c_void_p]),
     "srx_plan_build_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "srx_plan_cache_entries": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]),
     "srx_plan_set_grid": (C.c_int, [C.c_void_p, C.c_int]),

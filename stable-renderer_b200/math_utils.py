@@ -46,6 +46,46 @@ def tensor_group_by_then_average(t: torch.Tensor, index_column: int, value_colum
     return (out,)
 
 
+def tensor_group_by_then_randn_init(t: torch.Tensor, index_column: int, value_columns: list[int],
+                                    return_unique: bool = False, key_capacity: int | None = None,
+                                    generator: torch.Generator | None = None):
+    """`tensor_group_by_then_randn_init` (reference math_utils.py:164-229): rows that share `t[:, index_column]` receive
+    the same random row; returns the expanded random values (and the sorted unique keys when `return_unique`).
+
+    The reference sorts the keys (`unique(return_inverse=True)`), draws `torch.randn_like(unique.expand(-1, C), dtype=float)`
+    and indexes it with the inverse.  Here the inverse comes from a dense rank table on the GPU (bit-identical to the
+    sort's); the draw is the same torch call — one `[n_unique, C]` float32 normal draw on `t`'s device from `generator`
+    (default: the device's global generator, as in the reference) — so the values match the reference's on the same device."""
+    if index_column >= t.shape[-1]:
+        raise ValueError(f"Index column {index_column} is out of range.")
+    if any(col >= t.shape[-1] for col in value_columns):
+        raise ValueError(f"Value columns {value_columns} contain out of range values.")
+    if not t.is_cuda:
+        raise _lib.SrxUnavailable("tensor_group_by_then_randn_init needs a CUDA tensor (there is no CPU path)")
+    lib = _lib.load()
+    keys = t[:, index_column].to(torch.float32).contiguous()
+    n, c = int(keys.shape[0]), len(value_columns)
+    if n == 0:
+        out = torch.empty(0, c, dtype=torch.float32, device=t.device)
+        return (out, keys.unique()) if return_unique else (out,)
+    if key_capacity is None:
+        key_capacity = int(keys.max().item()) + 1
+    key_capacity = max(int(key_capacity), 1)
+    table = torch.empty(int(lib.srx_group_rank_workspace_ints(key_capacity)), dtype=torch.int32, device=t.device)
+    rank = torch.empty(n, dtype=torch.int32, device=t.device)
+    n_unique = C.c_int64(0)
+    with torch.cuda.device(t.device):
+        stream = _lib.current_stream_ptr(t.device)
+        _lib.check(lib.srx_group_rank(keys.data_ptr(), n, key_capacity, table.data_ptr(), rank.data_ptr(), C.byref(n_unique), stream))
+        random_values = torch.randn(int(n_unique.value), c, dtype=torch.float32, device=t.device, generator=generator)
+        out = torch.empty(n, c, dtype=torch.float32, device=t.device)
+        _lib.check(lib.srx_group_broadcast(random_values.data_ptr(), rank.data_ptr(), n, c, out.data_ptr(), stream))
+    if return_unique:
+        unique_values = torch.nonzero(table[:key_capacity] >= 0).flatten().to(t.dtype)
+        return out, unique_values
+    return (out,)
+
+
 def calc_map_mean_std(feat: torch.Tensor, eps: float = 1e-5):
     """`calc_map_mean_std` (reference math_utils.py:27-52): per (N, C) mean and sqrt(unbiased var + eps)."""
     assert feat.dim() == 4
@@ -71,4 +111,4 @@ def adaptive_instance_normalization(content_feat: torch.Tensor, style_feat: torc
     return normalized * style_std + style_mean
 
 
-__all__ = ["tensor_group_by_then_average", "calc_map_mean_std", "adaptive_instance_normalization"]
+__all__ = ["tensor_group_by_then_average", "tensor_group_by_then_randn_init", "calc_map_mean_std", "adaptive_instance_normalization"]
