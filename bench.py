@@ -463,7 +463,11 @@ def run_bake(args, rank: int, local: int, world: int) -> dict:
     nd = synthetic.make_normal_depth(V, H, H, device=dev, frame_offset=rank * V)
     cm = CorrespondMap(name="bench", k=1, height=tex, width=tex, channel_count=4, device=dev)
     K, Wm = args.steps, args.warmup
-    mode = dict(mode="replace", weight_mode=args.bake_weight, normal_depth=nd if args.bake_weight.startswith("view") else None)
+    if world > 1 and args.bake_weight == "none":
+        raise SystemExit("the reference bake modes are order dependent (last pixel wins): only the weighted bake shards over GPUs")
+    import torch.distributed as dist
+    mode = dict(mode="replace", weight_mode=args.bake_weight, normal_depth=nd if args.bake_weight.startswith("view") else None,
+                process_group=dist.group.WORLD if world > 1 else None)
     for _ in range(Wm):
         cm.update(colors, ids, **mode)
     barrier(world)
@@ -477,6 +481,24 @@ def run_bake(args, rank: int, local: int, world: int) -> dict:
     torch.cuda.synchronize()
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world) / K
+    # end to end through CorrespondMap.update with pinned host buffers: ids + colours (+ normal/depth) in, written flags out
+    host = [t.cpu().pin_memory() for t in (ids, colors)] + ([nd.cpu().pin_memory()] if mode["normal_depth"] is not None else [])
+    flags_out = torch.empty_like(cm._writtens, device="cpu").pin_memory()
+    n_e2e = 3
+
+    def e2e_step():
+        d = [t.to(dev, non_blocking=True) for t in host]
+        cm.update(d[1], d[0], **{**mode, "normal_depth": d[2] if len(d) > 2 else None})
+        flags_out.copy_(cm._writtens, non_blocking=True)
+
+    e2e_step()
+    barrier(world)
+    tw = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    barrier(world)
+    e2e_ms = max_over_ranks((time.perf_counter() - tw) * 1e3, world) / n_e2e
     clocks = sampler.stop()
     peak, peak_src = measured_hbm_peak()
     weighted = args.bake_weight != "none"
@@ -488,11 +510,35 @@ def run_bake(args, rank: int, local: int, world: int) -> dict:
         "config": {"workload": f"cfg4 bake: {views_total} views {H}x{H} RGB f32 -> {tex}x{tex} fp16 RGBA atlas, weight {args.bake_weight}",
                    "views_per_gpu": V, "l2": "inputs per step (ids+colours) are 1.9 GB/GPU at N=1, far above the 126 MB L2"},
         "texels_per_sec": views_total * H * H * 1e3 / ms, "clocks": clocks,
-        "e2e": None, "gpu_launches": 2 * K,
+        "e2e": {"value": views_total * 1e3 / e2e_ms, "unit": "views/s", "ms_per_step": e2e_ms, "steps": n_e2e,
+                "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host),
+                "d2h_bytes_per_step": flags_out.numel(), "api": "CorrespondMap.update(color_frames, id_maps, ...)"},
+        "gpu_launches": 2 * K,
         "roofline": {"bound": "hbm", "kernel": "k_bake_accum + k_bake_finalize" if weighted else "k_bake_claim + k_bake_write",
                      "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
                      "traffic": None, "peak_source": peak_src, "bytes_per_launch": alg},
     }
+
+
+def cpu_bake_baseline(views: int = 4) -> dict:
+    """The reference's CPU bake (oracle/torch_port.py::cpu_bake_port = CorrespondMap.update, mode 'replace') on a few views
+    of the cfg4 shape; the reference has no weighted bake, so this is the closest CPU counterpart."""
+    from stable_renderer_b200 import synthetic
+    from torch_port import cpu_bake_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    H, tex = 1024, 4096
+    ids = synthetic.make_ids(views, H, H, tex_h=tex, tex_w=tex, k=1, frac_2048=0.0, seed=99)
+    colors = torch.rand(views, H, H, 3)
+    masks = ((ids[..., 2] == 2048) | (ids == 0).all(-1)).float()
+    values = torch.zeros(1, tex * tex, 4, dtype=torch.float16)
+    writtens = torch.zeros(1, tex * tex, dtype=torch.bool)
+    cpu_bake_port(values, writtens, colors[:1], ids[:1], masks[:1])
+    t0 = time.perf_counter()
+    cpu_bake_port(values, writtens, colors, ids, masks)
+    dt = time.perf_counter() - t0
+    return {"value": views / dt, "unit": "views/s", "cores": cores, "kind": "port",
+            "sample": f"{views} of 64 views of cfg4 through CorrespondMap.update semantics (mode replace, unweighted), {dt * 1e3:.0f} ms"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -547,6 +593,8 @@ def main():
     else:
         out = run_overlap(args, rank, local, world)
     if rank == 0:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "bake":
+            out["cpu_baseline"] = cpu_bake_baseline()
         if world == 1 and not args.no_cpu_baseline and args.workload != "bake":
             out["cpu_baseline"] = cpu_overlap_baseline(args.workload, budget_s=12.0, max_steps=40,
                                                        frames_cap=32 if args.workload in ("cfg3", "cfg5") else None)

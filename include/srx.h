@@ -263,6 +263,10 @@ typedef struct srx_bake_args {
     const void *normal_depth_dev; /* fp16 [F,H,W,4] for the VIEW_NORMAL* weights */
     void *workspace_dev;       /* srx_bake_workspace_bytes() bytes */
     int64_t workspace_bytes;
+    int phase;                 /* weighted bake only: 0 = accumulate + finalize (default); 1 = clear + accumulate the weighted
+                                  sums of these views into the workspace; 2 = finalize the atlas from the workspace.  View-sharded
+                                  multi-GPU bakes run phase 1 per rank, sum the first srx_bake_workspace_bytes() - 256 bytes of
+                                  the workspaces as float32 (all-reduce), then phase 2 on every rank. */
 } srx_bake_args;
 int64_t srx_bake_workspace_bytes(int k2, int texels, int channels, int weight_mode);
 /* Errors with SRX_ERR_INDEX (after a sync) when a kept pixel addresses a texel outside the atlas. */

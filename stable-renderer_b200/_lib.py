@@ -70,7 +70,7 @@ class srx_bake_args(C.Structure):
                 ("ids_dev", C.c_void_p), ("id_dtype", C.c_int), ("masks_dev", C.c_void_p), ("inverse_masks", C.c_int),
                 ("frames", C.c_int), ("height", C.c_int), ("width", C.c_int), ("sprite_id", C.c_int),
                 ("material_id", C.c_int), ("ignore_obj_mat_id", C.c_int), ("mode", C.c_int), ("weight_mode", C.c_int),
-                ("normal_depth_dev", C.c_void_p), ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("normal_depth_dev", C.c_void_p), ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_int64), ("phase", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol of include/srx.h is listed (tests check the export table against it)

@@ -239,11 +239,15 @@ class CorrespondMap:
     # -- the bake ------------------------------------------------------------------------------------------------
     def update(self, color_frames, id_maps, spriteID: int | None = None, materialID: int | None = None,
                mode: UpdateMode = "first_avg", masks=None, inverse_masks: bool = False, ignore_obj_mat_id: bool = False,
-               weight_mode: BakeWeight = "none", normal_depth: Optional[Tensor] = None):
+               weight_mode: BakeWeight = "none", normal_depth: Optional[Tensor] = None, process_group=None,
+               phase: int = 0):
         """`CorrespondMap.update` (reference corrmap.py:578-670): same arguments; all frames go to the GPU in one call.
 
         weight_mode / normal_depth select the depth/normal-weighted multi-view bake, which the
-        reference lists as TODO (README.md:18-19); "none" is the reference behaviour."""
+        reference lists as TODO (README.md:18-19); "none" is the reference behaviour.
+        process_group: view-sharded multi-GPU bake (weighted modes only): every rank accumulates its own views, the
+        weighted sums are all-reduced, every rank finalises the same atlas.  `phase` (1 accumulate / 2 finalise) exposes
+        the two halves for callers that do the exchange themselves."""
         if mode not in ("replace", "replace_avg", "first", "first_avg"):
             raise ValueError(f"unknown update mode {mode}")
         colors = self._stack(color_frames, "color_frames")
@@ -307,8 +311,24 @@ class CorrespondMap:
         a.weight_mode = wm
         a.normal_depth_dev = nd.data_ptr() if nd is not None else None
         a.workspace_dev, a.workspace_bytes = self._workspace.data_ptr(), self._workspace.numel()
+        sharded = process_group is not None
+        if sharded:
+            import torch.distributed as dist
+            sharded = dist.get_world_size(process_group) > 1
+        if sharded and wm == 0:
+            raise _lib.SrxError("view-sharded bakes need a weight_mode: the reference modes keep the LAST pixel in frame order, "
+                                "which is not a sum (SURVEY.md §8e)")
         with torch.cuda.device(self.device):
-            _lib.check(lib.srx_bake_update(C.byref(a), _lib.current_stream_ptr(self.device)))
+            stream = _lib.current_stream_ptr(self.device)
+            if sharded:
+                a.phase = 1
+                _lib.check(lib.srx_bake_update(C.byref(a), stream))
+                dist.all_reduce(self._workspace[:need - 256].view(torch.float32), op=dist.ReduceOp.SUM, group=process_group)
+                a.phase = 2
+                _lib.check(lib.srx_bake_update(C.byref(a), stream))
+            else:
+                a.phase = int(phase)
+                _lib.check(lib.srx_bake_update(C.byref(a), stream))
 
     @staticmethod
     def _stack(frames, what: str) -> Tensor:

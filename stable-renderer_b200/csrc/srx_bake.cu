@@ -183,16 +183,20 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
         float *acc = reinterpret_cast<float *>(ws);
         float *wsum = reinterpret_cast<float *>(ws + bk_align(ntex * 16));
         status = reinterpret_cast<int *>(ws + bk_align(ntex * 16) + bk_align(ntex * 4));
-        SRX_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)(bk_align(ntex * 16) + bk_align(ntex * 4) + 256), st));
-        g.frames_total = a->frames;
-        const long long npx = (long long)a->frames * hw;
-        long long nb = (npx + 255) / 256;
-        const int grid = (int)(nb < (long long)sms * 8 ? nb : (long long)sms * 8);
-        k_bake_accum<IdT, CT><<<grid, 256, 0, st>>>(ids, a->masks_dev, colors, reinterpret_cast<const __half *>(a->normal_depth_dev),
-                                                    acc, wsum, status, g, a->weight_mode, npx);
-        long long nb2 = (ntex + 255) / 256;
-        const int grid2 = (int)(nb2 < (long long)sms * 8 ? nb2 : (long long)sms * 8);
-        k_bake_finalize<<<grid2, 256, 0, st>>>(acc, wsum, values, a->writtens_dev, ntex, g.C, g.first_mode);
+        if (a->phase != 2) {
+            SRX_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)(bk_align(ntex * 16) + bk_align(ntex * 4) + 256), st));
+            g.frames_total = a->frames;
+            const long long npx = (long long)a->frames * hw;
+            long long nb = (npx + 255) / 256;
+            const int grid = (int)(nb < (long long)sms * 8 ? nb : (long long)sms * 8);
+            k_bake_accum<IdT, CT><<<grid, 256, 0, st>>>(ids, a->masks_dev, colors, reinterpret_cast<const __half *>(a->normal_depth_dev),
+                                                        acc, wsum, status, g, a->weight_mode, npx);
+        }
+        if (a->phase != 1) {
+            long long nb2 = (ntex + 255) / 256;
+            const int grid2 = (int)(nb2 < (long long)sms * 8 ? nb2 : (long long)sms * 8);
+            k_bake_finalize<<<grid2, 256, 0, st>>>(acc, wsum, values, a->writtens_dev, ntex, g.C, g.first_mode);
+        }
     }
     SRX_CUDA_CHECK(cudaGetLastError());
     int st_host = 0;
@@ -221,6 +225,8 @@ extern "C" int srx_bake_update(const srx_bake_args *a, void *stream) {
     SRX_REQUIRE(a->frames > 0 && a->height > 0 && a->width > 0 && a->color_channels > 0, SRX_ERR_INVALID, "non-positive dimension");
     SRX_REQUIRE(a->mode >= SRX_BAKE_REPLACE && a->mode <= SRX_BAKE_FIRST_AVG, SRX_ERR_INVALID, "unknown update mode");
     SRX_REQUIRE(a->weight_mode >= SRX_WEIGHT_NONE && a->weight_mode <= SRX_WEIGHT_VIEW_NORMAL_DEPTH, SRX_ERR_INVALID, "unknown weight mode");
+    SRX_REQUIRE(a->phase >= 0 && a->phase <= 2 && (a->phase == 0 || a->weight_mode != SRX_WEIGHT_NONE), SRX_ERR_INVALID,
+                "phase 1/2 exist for the weighted bake only");
     // channel fix-up (corrmap.py:681-684): truncate, or append alpha = 1 when C == 4 and the colour has 3 channels
     SRX_REQUIRE(a->color_channels >= a->channels || (a->channels == 4 && a->color_channels == 3), SRX_ERR_INVALID,
                 "shape mismatch: colour has %d channels, atlas has %d", a->color_channels, a->channels);

@@ -109,3 +109,32 @@ def test_weighted_multi_view_bake_vs_oracle(weight_mode):
     assert np.array_equal(cm._writtens.cpu().numpy(), writtens)
     # float32 atomics vs float64 sums, then one fp16 rounding: allow one fp16 ulp (2^-11 relative)
     assert_close(t2n(cm._values), values.astype(np.float32), 1e-3, 1e-6, weight_mode)
+
+
+def test_weighted_bake_sharded_phases_equal_single_bake():
+    """View-sharded multi-GPU bake emulated on one GPU: two maps accumulate half of the views each (phase 1), the weighted
+    sums are added (what the all-reduce does), both finalise (phase 2) -> the atlas of one bake over all views."""
+    import torch
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import CorrespondMap
+    F, H, tex = 6, 128, 64
+    ids = synthetic.make_ids(F, H, H, tex_h=tex, tex_w=tex, k=1, seed=3).cuda()
+    colors = synthetic.make_colors(F, H, H, 3, seed=4).cuda()
+    nd = synthetic.make_normal_depth(F, H, H).cuda()
+    kw = dict(mode="replace", weight_mode="view_normal_depth")
+    ref = CorrespondMap(name="ref", k=1, height=tex, width=tex, channel_count=4)
+    ref.update(colors, ids, normal_depth=nd, **kw)
+    parts = []
+    for r in range(2):
+        sl = slice(r * F // 2, (r + 1) * F // 2)
+        cm = CorrespondMap(name=f"p{r}", k=1, height=tex, width=tex, channel_count=4)
+        cm.update(colors[sl], ids[sl], normal_depth=nd[sl], phase=1, **kw)
+        parts.append(cm)
+    n = parts[0]._workspace.numel() - 256
+    total = parts[0]._workspace[:n].view(torch.float32) + parts[1]._workspace[:n].view(torch.float32)
+    for r, cm in enumerate(parts):
+        sl = slice(r * F // 2, (r + 1) * F // 2)
+        cm._workspace[:n].view(torch.float32).copy_(total)
+        cm.update(colors[sl], ids[sl], normal_depth=nd[sl], phase=2, **kw)
+        assert torch.equal(cm._writtens, ref._writtens)
+        assert torch.allclose(cm._values.float(), ref._values.float(), rtol=2e-3, atol=2e-3)
