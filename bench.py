@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import sys
@@ -295,36 +296,50 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
     cached = None
     if fused_kernel:
         job_steps = 20
+        # J independent sampling runs (own plan, pool, latents, accumulators) stepped round-robin, so that between two
+        # steps of one run more than an L2's worth of other runs' data passes through: every cached step finds its
+        # pool / latents / accumulators in HBM, as it would after a UNet forward.
+        plans, xs_j = [plan], [x]
         plan.build_cache(ids_rot[0])
         kept, seen = plan.cache_entries()
+        # footprint of one run, from rank-independent sizes (all ranks must build the same number of plans): two
+        # accumulators, latents in + out, winners, and the pool estimated at 0.15 pairs per id pixel (cfg2 keeps 0.15)
+        per_job = 2 * acc.numel() * 4 + 2 * x.numel() * elem + 4 * F * h * h + int(8 * 0.15 * F * H * H)
+        n_jobs = max(2, min(24, int(math.ceil(1.5 * 126e6 / max(per_job, 1))) + 1))
+        for j in range(1, n_jobs):
+            pj = OverlapPlan(None, x.shape, id_shape=ids0.shape, id_dtype=ids0.dtype, key_capacity=key_capacity, device=dev,
+                             process_group=dist.group.WORLD if world > 1 else None, exchange=args.exchange)
+            plans.append(pj)
+            xs_j.append(x_init.clone())
         x.copy_(x_init)
-        for _ in range(5):
-            plan.step(x, RATIO, cached=True)
+
+        def run_jobs(build: bool):
+            if build:
+                for j, pj in enumerate(plans):
+                    pj.build_cache(ids_rot[j % n_rot])
+            for _ in range(job_steps):
+                for pj, xj in zip(plans, xs_j):
+                    pj.step(xj, RATIO, cached=True)
+
+        run_jobs(True)                                  # warm-up (also sizes the pools)
         barrier(world)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_c = 400
         c0.record()
-        for _ in range(n_c):
-            plan.step(x, RATIO, cached=True)
+        run_jobs(False)
         c1.record()
         torch.cuda.synchronize()
-        cached_ms = max_over_ranks(c0.elapsed_time(c1), world) / n_c
-        # whole jobs: bucketing pass on fresh ids (two id passes + one host sync for the pool size) + 20 cached steps
-        n_jobs = 6
-        x.copy_(x_init)
+        cached_ms = max_over_ranks(c0.elapsed_time(c1), world) / (job_steps * n_jobs)
         barrier(world)
         j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tw = time.perf_counter()
         j0.record()
-        for j in range(n_jobs):
-            plan.build_cache(ids_rot[j % n_rot])
-            for _ in range(job_steps):
-                plan.step(x, RATIO, cached=True)
+        run_jobs(True)
         j1.record()
         torch.cuda.synchronize()
         tw = (time.perf_counter() - tw) * 1e3
         job_ms = max_over_ranks(max(j0.elapsed_time(j1), tw), world) / n_jobs
-        pairs_bytes = 8 * kept
+        for pj in plans[1:]:
+            pj.close()
         cached = {"ms_per_step": cached_ms, "steps_per_sec": 1e3 / cached_ms,
                   "latent_px_per_sec": F_global * h * h * 1e3 / cached_ms,
                   "job": {"steps": job_steps, "ms": job_ms, "steps_per_sec": job_steps * 1e3 / job_ms,
@@ -332,9 +347,10 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
                           "includes": "bucketing pass on fresh ids (2 id passes, 1 host sync) + 20 cached steps, eager launches"},
                   "pairs_kept_per_gpu": kept, "pairs_seen_per_gpu": seen,
                   "algorithmic_bytes_per_step": 2 * F * 4 * h * h * elem + 8 * seen + 4 * F * h * h,
-                  "traffic_bytes_per_step": 2 * F * 4 * h * h * elem + pairs_bytes + 4 * F * h * h,
-                  "note": "ids unchanged between steps (SURVEY.md 8d cached-plan regime); pool and latents stay L2 resident "
-                          "between consecutive steps here — in the sampler a UNet forward runs in between"}
+                  "traffic_bytes_per_step": 2 * F * 4 * h * h * elem + 8 * kept + 4 * F * h * h,
+                  "l2": f"{n_jobs} independent runs of {per_job >> 20} MiB each stepped round-robin: no step finds its pool, "
+                        f"latents or accumulators in the 126 MB L2",
+                  "note": "ids unchanged between the steps of a run (SURVEY.md 8d cached-plan regime)"}
 
     # ---- end to end through the public API with host buffers ------------------------------------------------------
     class _Ctx:
