@@ -272,6 +272,14 @@ int64_t srx_bake_workspace_bytes(int k2, int texels, int channels, int weight_mo
 /* Errors with SRX_ERR_INDEX (after a sync) when a kept pixel addresses a texel outside the atlas. */
 int srx_bake_update(const srx_bake_args *args, void *stream);
 
+/* On-disk atlas format — the arithmetic of CorrespondMap.dump / Load (source/engine/static/corrmap.py:776-791, 846-858):
+ * uint8 = clip(255 * value, 0, 255) evaluated in float16 like numpy does, flags 0 / 255; and back: float32(u8) / 255 stored
+ * as float16, flag != 0.  The PNG / meta.json / zip handling stays in Python. */
+int srx_atlas_quantize(const void *values_f16_dev, const uint8_t *writtens_dev, uint8_t *out_values_dev, uint8_t *out_flags_dev,
+                       int64_t n_values, int64_t n_flags, void *stream);
+int srx_atlas_dequantize(const uint8_t *in_values_dev, const uint8_t *in_flags_dev, void *values_f16_dev, uint8_t *writtens_dev,
+                         int64_t n_values, int64_t n_flags, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Texture <-> tensor interop — replaces Texture._init_tensor/tensor/set_data (source/engine/static/texture/texture.py:166-254,
  * 326-408: pycuda RegisteredImage + Memcpy2D + torch.cuda.synchronize) and the cuda-python wrappers of

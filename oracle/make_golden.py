@@ -254,6 +254,26 @@ def randn_init_cases(R):
     save("noise_from_idmap", seed=np.int64(seed), id_seed=np.int64(17), tex=np.int64(96), size=np.int64(size), frames=np.int64(F), **out)
 
 
+def dump_cases(R):
+    """CorrespondMap.dump / Load (corrmap.py:738-872) on a small atlas with values outside [0,1] and halves that round."""
+    import tempfile
+    from PIL import Image
+    cmod = R["corrmap"]
+    m = cmod.CorrespondMap(name="t", k=2, height=8, width=16, channel_count=4)
+    g = torch.Generator().manual_seed(0)
+    m._values[:] = (torch.rand(4, 128, 4, generator=g) * 1.4 - 0.2).half()
+    m._writtens[:] = torch.rand(4, 128, generator=g) > 0.5
+    d = tempfile.mkdtemp()
+    with ref_shim.quiet():
+        p = m.dump(d, name="abc")
+        m2 = cmod.CorrespondMap.Load(p)
+    imgs = np.stack([np.array(Image.open(os.path.join(p, f"{i}.png"))) for i in range(4)])
+    flags = np.stack([np.array(Image.open(os.path.join(p, f"{i}_written.png"))) for i in range(4)])
+    meta = open(os.path.join(p, "meta.json")).read()
+    save("corrmap_dump", values=m._values.numpy().view(np.uint16), writtens=m._writtens.numpy(), png=imgs, png_written=flags,
+         loaded_values=m2._values.numpy().view(np.uint16), loaded_writtens=m2._writtens.numpy(), meta=np.array(meta))
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit("reference tree not mounted; fixtures can only be regenerated in the build container")
@@ -261,6 +281,7 @@ def main():
     R = ref_shim.load_reference()
     group_cases(R)
     randn_init_cases(R)
+    dump_cases(R)
     step_cases(R)
     bake_cases(R)
     legacy_cases(R)

@@ -553,3 +553,27 @@ def noise_sequence_from_ids(ids: np.ndarray, frame_indices: Optional[Sequence[in
            "min": lambda a: a.min(axis=(1, 2))}[downsample_option]
     noise = red(noise.reshape(-1, 4, 8, 8)).reshape(-1, 4, h, h)
     return np.zeros_like(noise), noise
+
+
+# =====================================================================================================
+# On-disk atlas format (corrmap.py:738-872) — the arithmetic of dump / Load
+# =====================================================================================================
+def corrmap_dump_arrays(values: np.ndarray, writtens: np.ndarray, height: int, width: int):
+    """What ``CorrespondMap.dump`` writes into the PNGs (corrmap.py:776-791): per map index
+    ``np.clip(255. * map, 0, 255).astype(np.uint8)`` — the product is evaluated in float16 because ``map`` is a float16
+    array and 255. a Python scalar — and the written flags as 0 / 255."""
+    k2, _, C = values.shape
+    v16 = np.asarray(values, dtype=np.float16).reshape(k2, height, width, C)
+    img = np.clip(np.float16(255.0) * v16, 0, 255).astype(np.uint8)
+    fl = np.clip(255.0 * np.asarray(writtens).reshape(k2, height, width).astype(np.float32), 0, 255).astype(np.uint8)
+    return img, fl
+
+
+def corrmap_load_arrays(img: np.ndarray, flags: np.ndarray):
+    """What ``CorrespondMap.Load`` reads back (corrmap.py:846-858): ``float32(u8) / 255.`` stored into the float16
+    ``_values``; ``(flag / 255.).bool()``."""
+    k2 = img.shape[0]
+    C = img.shape[-1] if img.ndim == 4 else 1
+    vals = (img.astype(np.float32) / np.float32(255.0)).astype(np.float16).reshape(k2, -1, C)
+    wr = (flags.astype(np.float32) / np.float32(255.0)) != 0
+    return vals, wr.reshape(k2, -1)

@@ -350,6 +350,99 @@ class CorrespondMap:
             return torch.cat(parts, dim=0)
         raise ValueError(f"Invalid type of {what}. Got: ", type(frames))
 
+    # -- on-disk format (reference corrmap.py:738-872) -------------------------------------------------------------
+    def dump(self, path, name: Optional[str] = None, zip: bool = False, force: bool = False):
+        """`CorrespondMap.dump`: k*k `{i}.png` (uint8 = clip(255*value)) + `{i}_written.png` + `meta.json` in a folder
+        (or a zip).  Same naming rules as the reference: without `force` an existing name gets a `_N` suffix, with
+        `force` the old folder / file is removed first.  The quantisation runs on the GPU; only bytes are copied back."""
+        import json
+        import shutil
+        import tempfile
+        import zipfile
+        from PIL import Image
+        name = name or self.name
+        real_name = name
+        suffix = ".zip" if zip else ""
+        path = str(path)
+        if not force:
+            count = 1
+            while os.path.exists(os.path.join(path, real_name + suffix)):
+                real_name = f"{name}_{count}"
+                count += 1
+        else:
+            old = os.path.join(path, real_name + suffix)
+            if os.path.exists(old):
+                if os.path.isdir(old):
+                    if zip:
+                        raise ValueError(f"Folder with the same name {real_name + suffix} already exists in {path}. "
+                                         "It is not allowed to delete a whole folder in zip mode.")
+                    shutil.rmtree(old)
+                else:
+                    os.remove(old)
+        real_path = os.path.join(path, real_name + suffix)
+        working = tempfile.mkdtemp(prefix="srx_corrmap_") if zip else real_path
+        os.makedirs(path, exist_ok=True)
+        os.makedirs(working, exist_ok=True)
+        k2, texels, ch = self.k * self.k, self.height * self.width, self.channel_count
+        q = torch.empty(k2 * texels * ch, dtype=torch.uint8, device=self.device)
+        fl = torch.empty(k2 * texels, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().srx_atlas_quantize(self._values.data_ptr(), self._writtens.data_ptr(), q.data_ptr(), fl.data_ptr(),
+                                                      q.numel(), fl.numel(), _lib.current_stream_ptr(self.device)))
+        q = q.view(k2, self.height, self.width, ch).cpu().numpy()
+        fl = fl.view(k2, self.height, self.width).cpu().numpy()
+        mode_map = {1: "L", 3: "RGB", 4: "RGBA"}
+        for i in range(k2):
+            img = q[i, :, :, 0] if ch == 1 else q[i]
+            Image.fromarray(img, mode=mode_map[ch]).save(os.path.join(working, f"{i}.png"))
+            Image.fromarray(fl[i], mode="L").save(os.path.join(working, f"{i}_written.png"))
+        with open(os.path.join(working, "meta.json"), "w") as f:
+            json.dump({"k": self.k, "height": self.height, "width": self.width, "channel_count": ch, "name": name}, f)
+        if zip:
+            with zipfile.ZipFile(real_path, "w") as z:
+                for i in range(k2):
+                    z.write(os.path.join(working, f"{i}.png"), f"{i}.png")
+                    z.write(os.path.join(working, f"{i}_written.png"), f"{i}_written.png")
+                z.write(os.path.join(working, "meta.json"), "meta.json")
+            shutil.rmtree(working)
+        return real_path
+
+    @classmethod
+    def Load(cls, path, name: Optional[str] = None, device=None):
+        """`CorrespondMap.Load`: folder or zip written by `dump` (values come back as uint8 / 255 in float16)."""
+        import json
+        import shutil
+        import tempfile
+        import zipfile
+        from PIL import Image
+        path = str(path)
+        tmp = None
+        real_path = path
+        if os.path.isfile(path):
+            tmp = tempfile.mkdtemp(prefix="srx_corrmap_")
+            with zipfile.ZipFile(path, "r") as z:
+                z.extractall(tmp)
+            real_path = tmp
+        try:
+            with open(os.path.join(real_path, "meta.json")) as f:
+                meta = json.load(f)
+            kw = {} if device is None else {"device": device}
+            m = cls(name=name or meta["name"], k=meta["k"], height=meta["height"], width=meta["width"],
+                    channel_count=meta["channel_count"], **kw)
+            k2 = m.k * m.k
+            vals = np.stack([np.array(Image.open(os.path.join(real_path, f"{i}.png"))).reshape(m.height, m.width, m.channel_count)
+                             for i in range(k2)])
+            flags = np.stack([np.array(Image.open(os.path.join(real_path, f"{i}_written.png"))) for i in range(k2)])
+        finally:
+            if tmp is not None:
+                shutil.rmtree(tmp)
+        vq = torch.from_numpy(np.ascontiguousarray(vals, dtype=np.uint8)).to(m.device)
+        fq = torch.from_numpy(np.ascontiguousarray(flags, dtype=np.uint8)).to(m.device)
+        with torch.cuda.device(m.device):
+            _lib.check(_lib.load().srx_atlas_dequantize(vq.data_ptr(), fq.data_ptr(), m._values.data_ptr(), m._writtens.data_ptr(),
+                                                        vq.numel(), fq.numel(), _lib.current_stream_ptr(m.device)))
+        return m
+
     def load_vertex_screen_info(self, id_map: IDMap):
         self.vertex_screen_info = id_map.create_vertex_screen_info()
 

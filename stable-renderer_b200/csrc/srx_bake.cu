@@ -237,3 +237,54 @@ extern "C" int srx_bake_update(const srx_bake_args *a, void *stream) {
     if (a->id_dtype == SRX_I16) return bake_color_dispatch<short4>(a, st);
     return srx_set_error(SRX_ERR_INVALID, "id dtype must be int32 or int16");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// On-disk atlas format (CorrespondMap.dump / Load, source/engine/static/corrmap.py:738-872): k*k PNGs of
+// uint8 = clip(255 * value, 0, 255) plus written-flag images.  The quantisation runs here so that only bytes cross PCIe.
+// numpy evaluates `255. * float16_array` in float16 (the product of two halves is exact in float32, so one rounding
+// to half reproduces it), clips, and truncates to uint8.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_atlas_to_u8(const __half *__restrict__ values, const unsigned char *__restrict__ writtens,
+                                                      unsigned char *__restrict__ out_values, unsigned char *__restrict__ out_flags,
+                                                      long long n_values, long long n_flags) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_values; i += (long long)gridDim.x * blockDim.x) {
+        const float p = __half2float(__float2half_rn(255.f * __half2float(values[i])));   // half product, as numpy
+        const float c = fminf(fmaxf(p, 0.f), 255.f);                                      // np.clip(img, 0, 255)
+        out_values[i] = (unsigned char)(int)c;                                            // .astype(np.uint8): truncation
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_flags; i += (long long)gridDim.x * blockDim.x)
+        out_flags[i] = writtens[i] ? 255 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_u8_to_atlas(const unsigned char *__restrict__ in_values, const unsigned char *__restrict__ in_flags,
+                                                      __half *__restrict__ values, unsigned char *__restrict__ writtens,
+                                                      long long n_values, long long n_flags) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_values; i += (long long)gridDim.x * blockDim.x)
+        values[i] = __float2half_rn(__fdiv_rn((float)in_values[i], 255.f));               // float32 / 255., stored as half
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_flags; i += (long long)gridDim.x * blockDim.x)
+        writtens[i] = in_flags[i] ? 1 : 0;                                                // (img / 255.).bool()
+}
+
+extern "C" int srx_atlas_quantize(const void *values_f16_dev, const uint8_t *writtens_dev, uint8_t *out_values_dev,
+                                  uint8_t *out_flags_dev, int64_t n_values, int64_t n_flags, void *stream) {
+    SRX_REQUIRE(values_f16_dev && writtens_dev && out_values_dev && out_flags_dev, SRX_ERR_INVALID, "null argument");
+    SRX_REQUIRE(n_values >= 0 && n_flags >= 0, SRX_ERR_INVALID, "bad sizes");
+    const long long nb = (n_values + 255) / 256;
+    const int grid = (int)(nb < 1 ? 1 : (nb < (long long)srx_sm_count_cached() * 8 ? nb : (long long)srx_sm_count_cached() * 8));
+    k_atlas_to_u8<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __half *>(values_f16_dev), writtens_dev,
+                                                                            out_values_dev, out_flags_dev, n_values, n_flags);
+    SRX_CUDA_CHECK(cudaGetLastError());
+    return SRX_OK;
+}
+
+extern "C" int srx_atlas_dequantize(const uint8_t *in_values_dev, const uint8_t *in_flags_dev, void *values_f16_dev,
+                                    uint8_t *writtens_dev, int64_t n_values, int64_t n_flags, void *stream) {
+    SRX_REQUIRE(values_f16_dev && writtens_dev && in_values_dev && in_flags_dev, SRX_ERR_INVALID, "null argument");
+    SRX_REQUIRE(n_values >= 0 && n_flags >= 0, SRX_ERR_INVALID, "bad sizes");
+    const long long nb = (n_values + 255) / 256;
+    const int grid = (int)(nb < 1 ? 1 : (nb < (long long)srx_sm_count_cached() * 8 ? nb : (long long)srx_sm_count_cached() * 8));
+    k_u8_to_atlas<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in_values_dev, in_flags_dev, reinterpret_cast<__half *>(values_f16_dev),
+                                                                            writtens_dev, n_values, n_flags);
+    SRX_CUDA_CHECK(cudaGetLastError());
+    return SRX_OK;
+}
