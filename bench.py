@@ -254,6 +254,8 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
     barrier(world)
     ms_total = max_over_ranks(ev0.elapsed_time(ev1), world)
     ms_step = ms_total / K
+    clocks = sampler.stop()        # clocks are sampled during the timed region of `value`; NVML polling would only
+                                   # perturb the host-driven end-to-end loops below
     plan.check()
     assert torch.isfinite(x.float()).all(), "latents became non-finite"
 
@@ -396,7 +398,51 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
     t_wall = time.perf_counter() - t_wall
     barrier(world)
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), t_wall * 1e3), world) / n_e2e
-    clocks = sampler.stop()
+    e2e_stream = {"value": F_global * h * h * 1e3 / e2e_ms, "unit": "latent-px/s",
+                  "h2d_bytes_per_step": id_bytes + x.numel() * elem, "d2h_bytes_per_step": x.numel() * elem,
+                  "ms_per_step": e2e_ms, "steps_per_sec": 1e3 / e2e_ms, "steps": n_e2e,
+                  "api": "OverlapCorresponder.step_finished(engine_data, sampling_context)",
+                  "regime": "every step brings a new id batch over PCIe (PCIe bound)"}
+
+    # The named config: one sampling run = one id batch + 20 denoise steps.  Per run the ids cross PCIe once; every step
+    # copies its latents in, calls step_finished (which buckets the ids on the first step and then runs from the cached
+    # plan) and copies the latents out.  This is also how the reference arm is timed (keying cached per id batch).
+    e2e_job = None
+    if fused_kernel:
+        job_steps, n_jobs = 20, 8
+        oc2 = OverlapCorresponder(step_finished_inject_ratio=RATIO, process_group=True if world > 1 else None,
+                                  exchange=args.exchange, cache_plan=True)
+        idm2 = IDMap(tensor=ids_dev, masks=torch.zeros(1, 1, 1))
+        ed2 = _ED()
+        ed2.id_maps, ed2.correspond_maps = idm2, {(1, 0): _MapSize()}
+        ctx2 = _Ctx()
+        ctx2.noise, ctx2.timestep, ctx2.total_steps = x_dev, 900, job_steps
+
+        def e2e_job_run(j: int):
+            ids_dev.copy_(ids_host[j % n_rot], non_blocking=True)
+            idm2.invalidate()
+            for s in range(job_steps):
+                ctx2.step_index = s
+                x_dev.copy_(x_host, non_blocking=True)
+                oc2.step_finished(ed2, ctx2)
+                x_out.copy_(x_dev, non_blocking=True)
+
+        e2e_job_run(0)
+        barrier(world)
+        t_wall = time.perf_counter()
+        for j in range(n_jobs):
+            e2e_job_run(j)
+        torch.cuda.synchronize()
+        t_wall = (time.perf_counter() - t_wall) * 1e3
+        barrier(world)
+        job_ms = max_over_ranks(t_wall, world) / n_jobs
+        e2e_job = {"value": F_global * h * h * job_steps * 1e3 / job_ms, "unit": "latent-px/s",
+                   "steps_per_sec": job_steps * 1e3 / job_ms, "ms_per_step": job_ms / job_steps, "ms_per_run": job_ms,
+                   "steps": job_steps * n_jobs,
+                   "h2d_bytes_per_step": id_bytes // job_steps + x.numel() * elem, "d2h_bytes_per_step": x.numel() * elem,
+                   "api": "OverlapCorresponder.step_finished(engine_data, sampling_context)",
+                   "regime": f"runs of {job_steps} denoise steps on one id batch: ids H2D once per run ({id_bytes >> 20} MiB, "
+                             "amortised above), latents H2D + D2H every step; wall clock"}
 
     out = {
         "metric": "overlap_latent_px_per_sec", "value": F_global * h * h * 1e3 / ms_step, "unit": "latent-px/s",
@@ -416,10 +462,10 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
         "overlap_steps_per_sec": 1e3 / ms_step,
         "id_px_per_sec": F_global * H * H * 1e3 / ms_step,
         "clocks": clocks,
-        "e2e": {"value": F_global * h * h * 1e3 / e2e_ms, "unit": "latent-px/s",
-                "h2d_bytes_per_step": id_bytes + x.numel() * elem, "d2h_bytes_per_step": x.numel() * elem,
-                "ms_per_step": e2e_ms, "steps_per_sec": 1e3 / e2e_ms, "steps": n_e2e,
-                "api": "OverlapCorresponder.step_finished(engine_data, sampling_context)"},
+        # `e2e` follows the named config (one id batch per 20 denoise steps — also how the reference arm is timed: keying
+        # cached per id batch); `e2e_every_step_new_ids` is the PCIe-bound worst case in which every step uploads new ids
+        "e2e": e2e_job if e2e_job is not None else e2e_stream,
+        "e2e_every_step_new_ids": e2e_stream,
         "cached_plan": cached,
         "gpu_launches": K if fused_kernel else (2 * K if plan.fast_path else 3 * K),
         "roofline": {"bound": "hbm", "kernel": k1_name,

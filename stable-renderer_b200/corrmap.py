@@ -158,6 +158,18 @@ class IDMap:
             self._device_ids[device] = t
         return t
 
+    def invalidate(self) -> None:
+        """The id buffers were overwritten in place (a new batch of frames in the same tensor): drop everything derived
+        from the old content.  The reference has the same staleness hazard in `_vertex_screen_info_cache`
+        (corrmap.py:226,278) and avoids it by building a new IDMap per batch; this keeps plans (and, frame-sharded, their
+        symmetric-memory workspaces) alive across batches."""
+        self._vertex_screen_info_cache = None
+        for plan in self._plans.values():
+            plan.cached = False
+            plan._calls = 0
+        same = self._device_ids.get(self.tensor.device) if isinstance(self.tensor, Tensor) else None
+        self._device_ids = {self.tensor.device: same} if same is not None and same.data_ptr() == self.tensor.data_ptr() else {}
+
     def create_vertex_screen_info(self) -> Tensor:
         """[N,7] float32 (object, material, map_index, vertex_id, x/H, y/W, frame_index) in (frame,y,x) order —
         bit-identical to the reference's tensor (corrmap.py:220-280), built by `srx_vertex_screen_info`."""
