@@ -448,18 +448,61 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             red_add_f32x4(acc + (long long)en.x * 4, fm * x0, fm * x1, fm * x2, fm * x3);
         }
     } else if (warp == FZ_CONS) {
-        // producer.  Items (8 id rows x 32 cells) are dealt round-robin in CHUNK-MAJOR order (all rows of column chunk
-        // 0, then chunk 1, ...): an item's cost follows the number of entries in it, which varies mostly with the
-        // screen position, and the SM count is a multiple of the usual chunks-per-row, so a row-major deal would hand
-        // the same (busy or empty) screen column to one CTA every time.  (A ticket counter in L2 balances no better
-        // and serialises: ~7 ns per same-address atomic is as long as an item takes to stream.)
+        // producer.  Items (8 id rows x 32 cells) are numbered in CHUNK-MAJOR order (all rows of column chunk 0, then
+        // chunk 1, ...): an item's cost follows the number of entries in it, which varies mostly with the screen
+        // position, and the SM count is a multiple of the usual chunks-per-row, so a row-major round-robin would hand the
+        // same (busy or empty) screen column to one CTA every time.  The first 70 % of the items are dealt round-robin;
+        // the rest is drawn in small batches from a ticket counter so that the CTAs finish together (a counter for ALL
+        // items serialises: ~7 ns per same-address atomic is as long as an item takes to stream).  Every CTA overdraws
+        // exactly one ticket, so the counter advances by a fixed amount per step and never needs a reset.  The bucketing
+        // passes (MARK / EMIT) must see identical deals, so they stay fully static.
         uint64_t pol;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
         int stage = 0;
         unsigned ph = 0;
         const char *ids = reinterpret_cast<const char *>(P.ids);
         const XT *x = reinterpret_cast<const XT *>(P.x);
-        for (unsigned item = blockIdx.x;; item += gridDim.x) {
+        const unsigned G = gridDim.x;
+        const bool dynamic_tail = P.mode == FZ_MODE_STEP;
+        const unsigned per_cta = dynamic_tail ? (nitems / G) * 70u / 100u : (nitems + G - 1) / G;
+        const unsigned static_end = dynamic_tail ? per_cta * G : nitems;
+        const unsigned rest = nitems - static_end;
+        // batches of 3..8 items: small enough that the last ones end within a few us of each other, large enough that the
+        // ticket counter (one same-address atomic per ~7.5 ns chip-wide) stays far from saturation
+        const unsigned batch = min(8u, max(3u, rest / (G * 8u)));
+        const unsigned nbatches = (rest + batch - 1) / batch;
+        unsigned *tickets = reinterpret_cast<unsigned *>(P.ws + P.ctrl_off + 8);
+        // tickets drawn by all earlier streaming steps (cached steps draw none, so this is not a function of `epoch`)
+        const unsigned tbase = *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off + 12) * (nbatches + G);
+        unsigned ticket = 0, next_ticket = 0, in_batch = 0;
+        unsigned k = 0;
+        bool drawing = false;
+        while (true) {
+            unsigned item;
+            if (!drawing) {
+                item = blockIdx.x + k * G;
+                ++k;
+                if (k > per_cta || item >= static_end) {          // static share done
+                    if (!dynamic_tail) item = nitems;
+                    else {
+                        drawing = true;
+                        if (lane == 0) ticket = atomicAdd(tickets, 1u) - tbase;
+                        ticket = __shfl_sync(FULL, ticket, 0);
+                        in_batch = 0;
+                    }
+                }
+            }
+            if (drawing) {
+                if (in_batch == batch) { ticket = __shfl_sync(FULL, next_ticket, 0); in_batch = 0; }
+                item = ticket < nbatches ? static_end + ticket * batch + in_batch : nitems;
+                if (item < nitems && in_batch == 0 && lane == 0) next_ticket = atomicAdd(tickets, 1u) - tbase;   // hides behind this batch
+                if (item >= nitems && ticket < nbatches) {       // ragged last batch: fetch the (overdrawn) next ticket
+                    ticket = __shfl_sync(FULL, next_ticket, 0);
+                    in_batch = 0;
+                    continue;
+                }
+                ++in_batch;
+            }
             mbar_wait(sbase + L::BAR_OFF + (FZ_STAGES + stage) * 8, ph ^ 1u);
             const uint32_t sb = sbase + stage * L::STAGE;
             const uint32_t full = sbase + L::BAR_OFF + stage * 8;
@@ -552,27 +595,41 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
                 if (lane == 0) P.winner[desc.x + cell] = (int)(wp & ((1u << FZ_SLOT_BITS) - 1u));
                 const unsigned lo = __reduce_min_sync(FULL, min((unsigned)a, (unsigned)b));
                 if (P.dbg & 1) continue;
-                if (P.mode != FZ_MODE_STEP) {
-                    // bucketing passes: the same reduce-by-key, but the (key, multiplicity) pairs are counted / stored
-                    const bool single = (int)lo == hi;
-                    const bool same = a == b;
-                    int ka1 = a, kb1 = same ? -1 : b, ma = same ? 2 : 1;
-                    if (single) {
-                        const int total = __reduce_add_sync(FULL, (a >= 0) + (b >= 0));
-                        ka1 = lane == 0 ? hi : -1;
-                        kb1 = -1;
-                        ma = total;
+                // reduce-by-key inside the warp -> up to two (key, multiplicity) pairs per lane:
+                //   * one key in the whole cell (REDUX min == max): a single pair for the cell;
+                //   * otherwise the lane's two horizontally adjacent pixels merge when equal, and vertically adjacent rows
+                //     (lane L = row 2i, lane L+4 = row 2i+1, same columns) merge pairwise through two shuffles.  Magnified
+                //     textures (several pixels per texel) are where this pays: every merge saves two L2 atomics.
+                int k1 = a, k2 = (a == b) ? -1 : b, m1 = (a == b) ? 2 : 1, m2 = 1;
+                if ((int)lo == hi) {
+                    const int total = __reduce_add_sync(FULL, (a >= 0) + (b >= 0));
+                    k1 = lane == 0 ? hi : -1;
+                    k2 = -1;
+                    m1 = total;
+                } else {
+                    const bool upper = (lane & 4) == 0;                       // even row of the cell
+                    const int o1 = __shfl_xor_sync(FULL, k1, 4), o2 = __shfl_xor_sync(FULL, k2, 4);
+                    const int om1 = __shfl_xor_sync(FULL, m1, 4);
+                    // first slots: same column pair, rows 2i / 2i+1.  Equal keys: the upper lane takes both.
+                    if (k1 >= 0 && o1 == k1) {
+                        if (upper) m1 += om1; else k1 = -1;
                     }
+                    if (k2 >= 0 && o2 == k2) {                                // second slots (multiplicity 1 on both sides)
+                        if (upper) m2 += 1; else k2 = -1;
+                    }
+                }
+                if (P.mode != FZ_MODE_STEP) {
+                    // bucketing passes: the pairs are counted / stored instead of reduced
                     if (P.mode == FZ_MODE_MARK) {
                         const int w = (int)(wp & ((1u << FZ_SLOT_BITS) - 1u));
-                        const int np = __popc(__ballot_sync(FULL, ka1 >= 0)) + __popc(__ballot_sync(FULL, kb1 >= 0));
+                        const int np = __popc(__ballot_sync(FULL, k1 >= 0)) + __popc(__ballot_sync(FULL, k2 >= 0));
                         if (lane == 0) {
                             P.need[w] = 1;
                             atomicAdd(s_fill, (unsigned)np);
                         }
                     } else {   // EMIT
-                        const bool fa = ka1 >= 0 && __ldg(P.need + ka1) != 0;
-                        const bool fb = kb1 >= 0 && __ldg(P.need + kb1) != 0;
+                        const bool fa = k1 >= 0 && __ldg(P.need + k1) != 0;
+                        const bool fb = k2 >= 0 && __ldg(P.need + k2) != 0;
                         const unsigned ba = __ballot_sync(FULL, fa), bb = __ballot_sync(FULL, fb);
                         const int tot = __popc(ba) + __popc(bb);
                         unsigned base = 0;
@@ -582,37 +639,25 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
                         const unsigned cellg = (unsigned)(desc.x + cell) << 6;
                         int2 *dst = P.pool + P.cta_tab[2 * gridDim.x + blockIdx.x] + base;
                         if (fa) {
-                            dst[__popc(ba & lt)] = make_int2(ka1, (int)(cellg | (unsigned)(ma - 1)));
-                            red_add_f32(P.cnt_plan + ka1, (float)ma);
+                            dst[__popc(ba & lt)] = make_int2(k1, (int)(cellg | (unsigned)(m1 - 1)));
+                            red_add_f32(P.cnt_plan + k1, (float)m1);
                         }
                         if (fb) {
-                            dst[__popc(ba) + __popc(bb & lt)] = make_int2(kb1, (int)(cellg | 0u));
-                            red_add_f32(P.cnt_plan + kb1, 1.f);
+                            dst[__popc(ba) + __popc(bb & lt)] = make_int2(k2, (int)(cellg | (unsigned)(m2 - 1)));
+                            red_add_f32(P.cnt_plan + k2, (float)m2);
                         }
                     }
                     continue;
                 }
-                if ((int)lo == hi) {                  // one key in the whole cell: a single reduction
-                    const int total = __reduce_add_sync(FULL, (a >= 0) + (b >= 0));
-                    if (lane == 0) {
-                        const float fm = (float)total;
-                        red_add_f32x4(acc + (long long)hi * 4, fm * xv[u][0], fm * xv[u][1], fm * xv[u][2], fm * xv[u][3]);
-                        red_add_f32(cnt + hi, fm);
-                    }
-                } else if (a == b) {                  // both valid and equal (a >= 0 here, otherwise hi < 0 or a != b)
-                    if (a >= 0) {
-                        red_add_f32x4(acc + (long long)a * 4, 2.f * xv[u][0], 2.f * xv[u][1], 2.f * xv[u][2], 2.f * xv[u][3]);
-                        red_add_f32(cnt + a, 2.f);
-                    }
-                } else {
-                    if (a >= 0) {
-                        red_add_f32x4(acc + (long long)a * 4, xv[u][0], xv[u][1], xv[u][2], xv[u][3]);
-                        red_add_f32(cnt + a, 1.f);
-                    }
-                    if (b >= 0) {
-                        red_add_f32x4(acc + (long long)b * 4, xv[u][0], xv[u][1], xv[u][2], xv[u][3]);
-                        red_add_f32(cnt + b, 1.f);
-                    }
+                if (k1 >= 0) {
+                    const float fm = (float)m1;
+                    red_add_f32x4(acc + (long long)k1 * 4, fm * xv[u][0], fm * xv[u][1], fm * xv[u][2], fm * xv[u][3]);
+                    red_add_f32(cnt + k1, fm);
+                }
+                if (k2 >= 0) {
+                    const float fm = (float)m2;
+                    red_add_f32x4(acc + (long long)k2 * 4, fm * xv[u][0], fm * xv[u][1], fm * xv[u][2], fm * xv[u][3]);
+                    red_add_f32(cnt + k2, fm);
                 }
             }
         }
@@ -628,7 +673,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
     FZ_TRACE(1);
     if (P.dbg & 4) {
         __syncthreads();
-        if (blockIdx.x == 0 && tid == 0) *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off) = epoch;
+        if (blockIdx.x == 0 && tid == 0) {   // (racy against slow producers: experiments only)
+            *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off) = epoch;
+            *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off + 12) += 1u;
+        }
         return;
     }
     fz_barrier(P, 0, target, true);    // every rank's reductions have landed in its own L2
@@ -642,7 +690,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         }                                                                                                          \
     } while (0)
     FZ_CTA_STAMP(0);
-    if (blockIdx.x == 0 && tid == 0) *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off) = epoch;
+    if (blockIdx.x == 0 && tid == 0) {
+        *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off) = epoch;
+        if (P.mode == FZ_MODE_STEP) *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off + 12) += 1u;   // streaming steps so far
+    }
 
     // ------------------------------------------------------------------------------------------------- phase X
     // Frame-sharded runs.  Rank r owns the slots [r*slice, (r+1)*slice): it PULLS the partial sums of its slice from
@@ -1047,6 +1098,7 @@ extern "C" int srx_plan_set_grid(srx_plan *p, int ctas) {
     SRX_REQUIRE(ctas >= 0 && ctas <= srx_sm_count_cached(), SRX_ERR_INVALID, "grid must be between 0 and the SM count");
     p->fused_grid = ctas;
     p->cache_ready = false;   // the cached plan is laid out per CTA
+    if (p->ws) SRX_CUDA_CHECK(cudaMemset(p->ws + p->ctrl_off + 8, 0, 8));   // ticket counter + streaming-step count depend on the grid
     return SRX_OK;
 }
 

@@ -96,6 +96,26 @@ def test_fused_consecutive_steps_and_graph_replay():
     assert_close(t2n(xg), want, 5e-5, 1e-5, "1 eager + 4 replayed steps")
 
 
+def test_fused_steps_with_changing_ids():
+    """Consecutive steps on DIFFERENT id batches (the streaming regime): a step that skipped or repeated work items would
+    leave winners of the previous batch behind or weigh frames twice."""
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.plan import OverlapPlan
+    F, H, tex = 6, 512, 256
+    ids0 = synthetic.make_ids(F, H, H, tex_h=tex, tex_w=tex, frac_2048=0.05, seed=8)
+    batches = [ids0, torch.roll(ids0, 1, 0).contiguous(), synthetic.make_ids(F, H, H, tex_h=tex, tex_w=tex, frac_2048=0.2, seed=9)]
+    x0 = synthetic.make_latents(F, 4, H // 8, H // 8, seed=3)
+    want = x0.numpy()
+    x = x0.cuda()
+    plan = OverlapPlan(None, x.shape, id_shape=ids0.shape, id_dtype=ids0.dtype, key_capacity=tex * tex, device=x.device)
+    dev_batches = [b.cuda() for b in batches]
+    for i in range(5):
+        want = O.overlap_step(want, batches[i % 3].numpy(), None, ratio=0.5, accumulate="f64")
+        plan.step(x, 0.5, ids=dev_batches[i % 3])
+        assert_close(t2n(x), want, 5e-5, 1e-5, f"step {i} on id batch {i % 3}")
+    plan.check()
+
+
 def test_fused_key_out_of_range_is_reported():
     from stable_renderer_b200 import _lib
     from stable_renderer_b200.plan import OverlapPlan
