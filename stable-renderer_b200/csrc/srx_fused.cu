@@ -681,15 +681,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
     }
     fz_barrier(P, 0, target, true);    // every rank's reductions have landed in its own L2
     FZ_TRACE(2);
-#define FZ_CTA_STAMP(idx)                                                                                          \
-    do {                                                                                                           \
-        if (tid == 0 && (epoch & 63u) == 40u) {                                                                    \
-            unsigned long long now_;                                                                               \
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                                               \
-            reinterpret_cast<unsigned long long *>(P.ws + P.ctrl_off + 4096)[blockIdx.x * 3 + idx] = now_;          \
-        }                                                                                                          \
-    } while (0)
-    FZ_CTA_STAMP(0);
     if (blockIdx.x == 0 && tid == 0) {
         *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off) = epoch;
         if (P.mode == FZ_MODE_STEP) *reinterpret_cast<volatile unsigned *>(P.ws + P.ctrl_off + 12) += 1u;   // streaming steps so far
@@ -727,7 +718,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         __syncthreads();
         FZ_TRACE(4);
     }
-    FZ_CTA_STAMP(1);
 
     // ------------------------------------------------------------------------------------------------- phases B, C
     // Each latent frame is handled by a group of `grp` CTAs (grp = gridDim / frames when there are fewer frames than
@@ -881,7 +871,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         __syncthreads();
     }
     FZ_TRACE(7);
-    FZ_CTA_STAMP(2);
     if (tid == 0) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -1121,7 +1110,6 @@ extern "C" int srx_plan_read_step_ring(srx_plan *p, uint64_t *out64, void *strea
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     SRX_CUDA_CHECK(cudaMemcpyAsync(out64, p->ws + p->ctrl_off + 256, 512, cudaMemcpyDeviceToHost, st));
     SRX_CUDA_CHECK(cudaMemcpyAsync(out64 + 64, p->ws + p->ctrl_off + 1024, 2048, cudaMemcpyDeviceToHost, st));
-    SRX_CUDA_CHECK(cudaMemcpyAsync(out64 + 320, p->ws + p->ctrl_off + 4096, 148 * 3 * 8, cudaMemcpyDeviceToHost, st));
     SRX_CUDA_CHECK(cudaStreamSynchronize(st));
     return SRX_OK;
 }

@@ -50,7 +50,7 @@ static inline void plan_layout(srx_plan *p) {
     p->pads_off = off;   // [3 barriers][SRX_MAX_PEERS sources] u32 arrival counters (monotonic)
     off += 256;
     p->ctrl_off = off;   // [0] step counter; +64 phase stamps of the first / last CTA; +256 ring of per-step (first CTA
-    off += 8192;         // start, last CTA end) global-timer stamps; +1024 ring of the first CTA's phase stamps (profiling aids)
+    off += 4096;         // start, last CTA end) global-timer stamps; +1024 ring of the first CTA's phase stamps (profiling aids)
     // peer mode: this rank's slice of exchanged totals, [ceil(K / world)] records of 32 B {sum.xyzw, count, step}; world >= 2
     p->ll_off = off;
     p->ll_bytes = p->fused ? (p->kcap / 2 + 64) * 32 : 0;

@@ -138,9 +138,8 @@ class OverlapPlan:
         return {"first_cta": v[:8], "last_cta": v[8:]}
 
     def read_step_ring(self) -> list:
-        buf = (C.c_uint64 * (320 + 148 * 3))()
+        buf = (C.c_uint64 * 320)()
         _lib.check(_lib.load().srx_plan_read_step_ring(self._handle, buf, _lib.current_stream_ptr(self.device)))
-        self.cta_stamps = [[int(buf[320 + 3 * i + j]) for j in range(3)] for i in range(148)]
         return [(int(buf[2 * i]), int(buf[2 * i + 1]), [int(buf[64 + 8 * i + j]) for j in range(8)]) for i in range(32)]
 
     def set_grid(self, ctas: int) -> None:

@@ -79,9 +79,6 @@ for _, _, st in ring[-16:]:
         ss_parts[j] += (st[j + 1] - st[j]) / mhz / 16
 ss_txt = ", ".join(f"{nm} {v:.1f}" for nm, v in zip(names, ss_parts))
 gaps = [(ring[i + 1][0] - ring[i][1]) / 1e3 for i in range(len(ring) - 1)]
-cs = plan.cta_stamps
-t0min = min(c[0] for c in cs if c[0])
-cta_txt = " ".join(f"{i}:{(c[1] - t0min) / 1e3:.0f}/{(c[2] - t0min) / 1e3:.0f}" for i, c in enumerate(cs) if c[0] and i % 6 == 0)
 tr = plan.read_trace()["first_cta"]
 last_span = (tr[7] - tr[0]) / mhz
 if world == 1:
@@ -96,7 +93,6 @@ for r in range(world):
             print(f"[rank {rank}] {wl} {key}: " + ", ".join(f"{nm} {v:.1f}" for nm, v in zip(names, acc[w])) +
                   f" | total {sum(acc[w]):.1f} us (exchange={plan.exchange})", flush=True)
         print(f"[rank {rank}] global-timer: kernel spans {[round(v, 1) for v in spans[-8:]]} us, gaps between kernels {[round(v, 1) for v in gaps[-8:]]} us; steady-state first-CTA phases: {ss_txt}", flush=True)
-        print(f"[rank {rank}] step 40 per-CTA (us after barrier0: X done / kernel end): {cta_txt}", flush=True)
         print(f"[rank {rank}] event-timed single launch {ev_ms * 1e3:.1f} us; 60 back-to-back launches {b2b:.1f} us/step "
               f"(in-kernel span of the last one {last_span:.1f} us: {b2b_parts})", flush=True)
     if world > 1:
