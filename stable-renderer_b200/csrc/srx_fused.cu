@@ -9,15 +9,19 @@
 //   A  stream   : a producer warp keeps a ring of FZ_STAGES shared-memory stages full with bulk async copies
 //                 (cp.async.bulk -> UBLKCP, completion on an mbarrier): per stage 8 id rows x 32 cells (32 KB of ids,
 //                 L2 evict-first: read once) plus the 32 cells' latents.  Sixteen consumer warps key the pixels out of
-//                 shared memory (a warp per cell, two adjacent pixels per lane), reduce equal keys inside the warp with
-//                 REDUX, and issue one 128-bit vector reduction + one count reduction per distinct key into the
-//                 L2-resident accumulator; the cell's last valid pixel is its winner.  While the first copies are in
-//                 flight the consumers clear the accumulator of the NEXT step (double buffered by step parity).
-//   X  exchange : (frame-sharded runs) every CTA signals every peer; rank r then owns a 1/world slice of the
-//                 accumulator: it loads that slice from all peers, adds in rank order and stores the total back into
-//                 every peer — reduce-scatter and all-gather in one pass over NVLink, 2 signal rounds, no NCCL call.
-//   B  gather   : cells are split evenly over the CTAs: winner's mean, blend, per-frame sums of x, x^2, b, b^2 (double)
-//   C  AdaIN    : after one more grid-wide barrier: re-standardise x in place.
+//                 shared memory (a warp per cell, two adjacent pixels per lane), reduce equal keys inside the warp
+//                 (REDUX for single-key cells, in-lane and row-pair merges otherwise) and issue one 128-bit vector
+//                 reduction + one count reduction per distinct key into the L2-resident accumulator; the cell's last
+//                 valid pixel is its winner.  While the first copies are in flight the consumers clear the accumulator
+//                 of the NEXT step (double buffered by step parity).  In the cached-plan regime this phase reads the
+//                 (key, cell, multiplicity) pairs stored by the bucketing passes (MARK / EMIT modes) instead of the ids.
+//   X  exchange : (frame-sharded runs) after a box-wide barrier rank r PULLS the partial sums of its 1/world slice of
+//                 the accumulator from every peer over NVLink, adds them in rank order and keeps the totals as 32-byte
+//                 flagged records in its own memory; one signal round later everybody fetches the records it needs
+//                 from their owners.  Only arrival counters are ever stored to a peer; no NCCL call.
+//   B  gather   : each latent frame is handled by a group of CTAs: winner's mean, blend, sums of x, x^2, b, b^2 (double)
+//   C  AdaIN    : the CTAs of a frame exchange their sums and meet at the frame's own counter, then re-standardise x
+//                 in place (the latents stay in shared memory between B and C).
 // Barriers are monotonic arrival counters in the workspace (targets derive from a device-side step counter, so the
 // kernel replays unchanged from a CUDA graph); the launch is cooperative so that all CTAs are co-resident.
 #include "srx_plan.cuh"
@@ -35,9 +39,9 @@
 enum { FZ_ST_KEY_RANGE = 0 };
 // What the kernel does with the ids:
 //   STEP    the streaming overlap step (ids new for this call)
-//   MARK    bucketing pass 1 — phase A only: winners, the bitmap of winner keys, pairs per CTA.  No reductions.
+//   MARK    bucketing pass 1 — phase A only: winners, the byte map of winner keys, pairs per CTA.  No reductions.
 //   EMIT    bucketing pass 2 — phase A only: every CTA appends the (key, cell, multiplicity) pairs whose key is in the
-//           bitmap to its own region of the pool (same static deal of items as MARK, so the MARK counts bound the regions)
+//           map to its own region of the pool (same static deal of items as MARK, so the MARK counts bound the regions)
 //   CACHED  the overlap step from the pool: no id traffic; reductions only for keys that matter
 enum { FZ_MODE_STEP = 0, FZ_MODE_MARK = 1, FZ_MODE_EMIT = 2, FZ_MODE_CACHED = 3 };
 
