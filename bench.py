@@ -585,6 +585,69 @@ def run_bake(args, rank: int, local: int, world: int) -> dict:
     }
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# legacy overlap workload: ResizeOverlap with the four weighting strategies
+# ---------------------------------------------------------------------------------------------------------------------
+def run_legacy(args, rank: int, local: int, world: int) -> dict:
+    from stable_renderer_b200 import _lib, synthetic
+    from stable_renderer_b200.overlap import CorrespondenceMap, ResizeOverlap, Scheduler, overlap_algorithm_factory
+    if world > 1:
+        raise SystemExit("the legacy overlap keeps per-key group members, not sums: replicas only (SURVEY.md §8e)")
+    _lib.load()
+    F, H, h = 16, 512, 64
+    dev = torch.device("cuda", local)
+    ids = [synthetic.make_ids(F, H, H, tex_h=512, tex_w=512, seed=1234 + r, device=dev, legacy_layout=True) for r in range(3)]
+    cms = [CorrespondenceMap(t) for t in ids]                 # three id batches of 64 MiB rotate (larger than L2 together)
+    frames = [synthetic.make_latents(1, 4, h, h, seed=i).to(dev) for i in range(F)]
+    vn = torch.rand(F, H, H, 1, device=dev)
+    alpha = Scheduler(interpolate_begin=0.9, interpolate_end=0.9, interpolate_type="constant")
+    radius = Scheduler(interpolate_begin=0, interpolate_end=0, interpolate_type="constant")
+    K, Wm = max(args.steps // 20, 20), args.warmup
+    per = {}
+    for name in ("average", "frame_distance", "pixel_distance", "perpendicular_view_normal"):
+        ov = ResizeOverlap(alpha, radius, overlap_algorithm_factory(name), verbose=False)
+        kw = {"view_normal_map": vn} if name == "perpendicular_view_normal" else {}
+        for i in range(Wm):
+            ov(frames, cms[i % 3], step=1, timestep=900, **kw)
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            ov(frames, cms[i % 3], step=1, timestep=900, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        per[name] = e0.elapsed_time(e1) / K
+    peak, peak_src = measured_hbm_peak()
+    alg = 16 * F * H * H + 2 * F * 4 * h * h * 4
+    ms = per["average"]
+    return {"metric": "legacy_overlap_latent_px_per_sec", "value": F * h * h * 1e3 / ms, "unit": "latent-px/s", "n_gpus": 1,
+            "steps": K, "warmup": Wm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"legacy ResizeOverlap.__call__: {F} frames of {H}x{H}x4 int32 (obj, mat, texX, texY) ids -> "
+                                   f"{h}x{h}x4 f32 latents, alpha 0.9, radius 0; value = strategy 'average'",
+                       "l2": "three id batches of 64 MiB rotate"},
+            "ms_per_step_by_strategy": per, "e2e": None, "gpu_launches": 3 * K,
+            "roofline": {"bound": "hbm", "kernel": "k_legacy_seed + k_legacy_accum + k_legacy_finalize (whole call, incl. torch.stack)",
+                         "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": alg}}
+
+
+def cpu_legacy_baseline() -> dict:
+    """oracle restatement of the reference's per-trace Python loop (overlap.py:83-152) on a 2-frame 128x128 crop."""
+    import numpy as np
+    import srx_oracle as O
+    from stable_renderer_b200 import synthetic
+    F, H, h = 2, 128, 16
+    ids = synthetic.make_ids(F, H, H, tex_h=128, tex_w=128, seed=1234, legacy_layout=True).numpy()
+    x = np.random.default_rng(0).standard_normal((F, 1, 4, h, h))
+    t0 = time.perf_counter()
+    O.legacy_resize_overlap(x, ids, 0.9, "average")
+    dt = time.perf_counter() - t0
+    return {"value": F * h * h / dt, "unit": "latent-px/s", "cores": 1, "kind": "port",
+            "sample": f"{F} frames of {H}x{H} ids -> {h}x{h} latents, strategy average, {dt * 1e3:.0f} ms (the reference loops over "
+                      "every key in Python; work is proportional to the id pixels)"}
+
+
 def cpu_bake_baseline(views: int = 4) -> dict:
     """The reference's CPU bake (oracle/torch_port.py::cpu_bake_port = CorrespondMap.update, mode 'replace') on a few views
     of the cfg4 shape; the reference has no weighted bake, so this is the closest CPU counterpart."""
@@ -613,7 +676,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=list(WORKLOADS) + ["bake"], default="cfg2")
+    ap.add_argument("--workload", choices=list(WORKLOADS) + ["bake", "legacy"], default="cfg2")
     ap.add_argument("--bake-weight", default="view_normal_depth", choices=["none", "uniform", "view_normal", "view_normal_depth"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", choices=["auto", "peer", "nccl"], default="auto",
@@ -626,7 +689,7 @@ def main():
         # the reference's own CPU path for this metric/config; rank 0 alone runs it
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        wl = "cfg2" if args.workload == "bake" else args.workload
+        wl = "cfg2" if args.workload in ("bake", "legacy") else args.workload
         frames_cfg, H, h, dtype, tex, n_obj, scaling = WORKLOADS[wl]
         # bounded sample: enough frames per step that K + W steps end within ~2 minutes
         probe = cpu_overlap_baseline(wl, budget_s=2.0, max_steps=3, frames_cap=2)
@@ -655,12 +718,16 @@ def main():
     rank, local, world = init_dist(args.gpus)
     if args.workload == "bake":
         out = run_bake(args, rank, local, world)
+    elif args.workload == "legacy":
+        out = run_legacy(args, rank, local, world)
     else:
         out = run_overlap(args, rank, local, world)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline and args.workload == "bake":
             out["cpu_baseline"] = cpu_bake_baseline()
-        if world == 1 and not args.no_cpu_baseline and args.workload != "bake":
+        if world == 1 and not args.no_cpu_baseline and args.workload == "legacy":
+            out["cpu_baseline"] = cpu_legacy_baseline()
+        if world == 1 and not args.no_cpu_baseline and args.workload not in ("bake", "legacy"):
             out["cpu_baseline"] = cpu_overlap_baseline(args.workload, budget_s=12.0, max_steps=40,
                                                        frames_cap=32 if args.workload in ("cfg3", "cfg5") else None)
         print(json.dumps(out), flush=True)
