@@ -291,3 +291,53 @@ def test_cached_plan_peer_exchange_two_ranks_on_one_gpu():
                 plans[r].step(xs[r], 0.5, cached=True)
         torch.cuda.synchronize()
         assert_close(t2n(torch.cat(xs, dim=0)), t2n(ref), 2e-5, 5e-6, f"cached + peer exchange, step {step}")
+
+
+@pytest.mark.parametrize("frames", [5, 160])
+def test_fused_frame_grouping_paths(frames):
+    """Gather / AdaIN scheduling: 5 frames -> groups of 29 CTAs per frame with idle CTAs left over; 160 frames -> more
+    frames than CTAs, every CTA walks over several frames on its own (no statistics exchange)."""
+    from stable_renderer_b200.plan import OverlapPlan
+    H = 64
+    ids, x0 = _inputs(frames, H, H, 64, seed=frames)
+    want = O.overlap_step(x0.numpy(), ids.numpy(), None, ratio=0.4, accumulate="f64")
+    x = x0.cuda()
+    plan = OverlapPlan(ids.cuda(), x.shape, key_capacity=64 * 64)
+    assert plan.fused
+    plan.step(x, 0.4)
+    plan.check()
+    assert_close(t2n(x), want, RTOL, ATOL, f"{frames} frames")
+    plan.build_cache()
+    x2 = x0.cuda()
+    plan.step(x2, 0.4, cached=True)
+    assert_close(t2n(x2), want, RTOL, ATOL, f"{frames} frames, cached plan")
+
+
+def test_fused_peer_exchange_three_ranks_on_one_gpu():
+    """Three emulated ranks (a third of the SMs each): owner slices with a remainder (capacity 10,048 / 3), ring order of the
+    pulls, totals added in rank order."""
+    from stable_renderer_b200 import _lib
+    from stable_renderer_b200.plan import OverlapPlan
+    sms = _lib.load().srx_device_sm_count()
+    F, H, tex = 9, 128, 100
+    ids, x0 = _inputs(F, H, H, tex, seed=79)
+    ids = ids.cuda()
+    ref = x0.cuda()
+    cap = tex * tex + 48                       # 10,048 after rounding up to 64: not divisible by 3
+    pref = OverlapPlan(ids, ref.shape, key_capacity=cap)
+    xs = [x0[r * 3:(r + 1) * 3].contiguous().cuda() for r in range(3)]
+    plans = [OverlapPlan(ids[r * 3:(r + 1) * 3].contiguous(), xs[r].shape, key_capacity=cap) for r in range(3)]
+    ptrs = [p.workspace.data_ptr() for p in plans]
+    for r, p in enumerate(plans):
+        p.set_grid(sms // 3)
+        p.bind_peers(r, ptrs)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    for step in range(2):
+        pref.step(ref, 0.5)
+        torch.cuda.synchronize()
+        for r in range(3):
+            with torch.cuda.stream(streams[r]):
+                plans[r].step(xs[r], 0.5)
+        torch.cuda.synchronize()
+        assert_close(t2n(torch.cat(xs, dim=0)), t2n(ref), 2e-5, 5e-6, f"3-rank peer exchange, step {step}")
