@@ -237,6 +237,18 @@ int64_t srx_legacy_workspace_bytes(const srx_legacy_desc *desc);
 /* Errors (after a sync) with SRX_ERR_KEY_RANGE when an id component does not fit the packed 64-bit key. */
 int srx_legacy_overlap(const srx_legacy_desc *desc, const srx_legacy_args *args, void *stream);
 
+/* CorrespondenceMap maintenance (legacy data_classes/correspondence_map.py).  The map IS the id buffers: a key is the id
+ * tuple (after merge_nearby's floor division), deleting a key clears the ids of every pixel that carries it.
+ *   srx_corrmap_first_appearance: mask[i] = 1 where pixel i introduces its key — the marked pixels, in index order, are the
+ *       reference dict's keys in insertion order (:148-168); needed to replay dropout_index's random stream (:207-223).
+ *   srx_corrmap_drop_keys: delete the keys carried by the seed pixels (dropout_index :219-223, dropout_in_rectangle :268-274).
+ * Workspace: srx_corrmap_keys_workspace_bytes(F*H*W) for the first, (n_seeds) for the second.  Both sync. */
+int64_t srx_corrmap_keys_workspace_bytes(int64_t n_keys_upper_bound);
+int srx_corrmap_first_appearance(const void *ids_dev, int id_dtype, int frames, int height, int width, int merge_len,
+                                 uint8_t *mask_out_dev, void *workspace_dev, int64_t workspace_bytes, void *stream);
+int srx_corrmap_drop_keys(void *ids_dev, int id_dtype, int frames, int height, int width, int merge_len,
+                          const int64_t *seed_pixels_dev, int64_t n_seeds, void *workspace_dev, int64_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Bake — replaces CorrespondMap.update/_update (source/engine/static/corrmap.py:578-736)
  * ------------------------------------------------------------------------------------------------------------------ */

@@ -163,6 +163,20 @@ def legacy_cases(R):
     mflat = np.array([(p[0], p[1], f) for v in merged.Map.values() for (p, f) in v], dtype=np.int64)
     save("legacy_corrmap_merge4", keys=mkeys, lens=mlens, traces=mflat)
 
+    # dropouts (correspondence_map.py:207-274) on copies of the full and the merged map
+    drop = {}
+    for tag, base in (("full", cmap), ("merge4", merged)):
+        a = CorrespondenceMap(dict(base.Map), base.width, base.height, base.num_frames)
+        with ref_shim.quiet():
+            a.dropout_index(0.3, 5)
+        drop[f"{tag}_index_keys"] = np.array(list(a.Map.keys()), dtype=np.int64)
+        b = CorrespondenceMap(dict(base.Map), base.width, base.height, base.num_frames)
+        with ref_shim.quiet():
+            b.dropout_in_rectangle(((3, 4), (20, 25)), 1)
+        drop[f"{tag}_rect_keys"] = np.array(list(b.Map.keys()), dtype=np.int64)
+    save("legacy_corrmap_dropout", probability=np.float64(0.3), seed=np.int64(5), rect=np.array([[3, 4], [20, 25]]),
+         at_frame=np.int64(1), **drop)
+
     torch.manual_seed(0)
     frames = [torch.randn(1, 4, h, w, dtype=torch.float64) for _ in range(T)]
     vn = torch.rand(T, H, W, 1, dtype=torch.float64)

@@ -577,3 +577,30 @@ def corrmap_load_arrays(img: np.ndarray, flags: np.ndarray):
     vals = (img.astype(np.float32) / np.float32(255.0)).astype(np.float16).reshape(k2, -1, C)
     wr = (flags.astype(np.float32) / np.float32(255.0)) != 0
     return vals, wr.reshape(k2, -1)
+
+
+# =====================================================================================================
+# K5 maintenance: dropouts on the dict of traces (correspondence_map.py:207-274)
+# =====================================================================================================
+def traces_dropout_index(traces: Dict[tuple, list], probability: float, seed: int) -> Dict[tuple, list]:
+    """``dropout_index`` (:207-223): one ``random.random()`` per key in dict order; keys with a draw < p are deleted."""
+    import random
+    random.seed(seed)
+    out = dict(traces)
+    for key in list(out.keys()):
+        if random.random() < probability:
+            del out[key]
+    return out
+
+
+def traces_dropout_in_rectangle(traces: Dict[tuple, list], rectangle, at_frame: int) -> Dict[tuple, list]:
+    """``dropout_in_rectangle`` (:225-274): a key is deleted when one of its tracks at ``at_frame`` lies strictly inside
+    ``((r0, c0), (r1, c1))`` (positions are [row, col], :156-160)."""
+    (r0, c0), (r1, c1) = rectangle
+    out = dict(traces)
+    for key, tracks in traces.items():
+        for (r, c, f) in tracks:
+            if f == at_frame and r0 < r < r1 and c0 < c < c1:
+                del out[key]
+                break
+    return out

@@ -319,3 +319,171 @@ extern "C" int srx_legacy_overlap(const srx_legacy_desc *d, const srx_legacy_arg
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return d->id_dtype == SRX_I32 ? legacy_x_dispatch<int4>(d, a, st) : legacy_x_dispatch<short4>(d, a, st);
 }
+
+// =================================================================================================================
+// CorrespondenceMap maintenance on the id buffers: which pixel introduces a key (the reference dict's insertion
+// order), and dropping whole keys (dropout_index / dropout_in_rectangle, correspondence_map.py:207-274).
+// The "map" here is the id buffers themselves; deleting a key = clearing the ids of every pixel that carries it.
+// =================================================================================================================
+struct KeyTable {
+    unsigned long long *keys;   // [cap] packed id tuple, LG_EMPTY = free
+    unsigned long long *first;  // [cap] smallest linear pixel index that carries the key
+    unsigned int mask;
+};
+
+template <typename IdT>
+__device__ __forceinline__ bool km_key(const IdT *ids, long long i, int merge, unsigned long long *key, int *status) {
+    const IdPx p = load_id(ids + i);
+    if ((p.s | p.m | p.i | p.v) == 0) return false;              // correspondence_map.py:153
+    if (!pack_key<IdT>(p, merge, key)) { atomicOr(status, 1); return false; }
+    return true;
+}
+
+__device__ __forceinline__ unsigned int km_insert(const KeyTable &t, unsigned long long key) {
+    unsigned int s = hash64(key) & t.mask;
+    while (true) {
+        const unsigned long long prev = atomicCAS(t.keys + s, LG_EMPTY, key);
+        if (prev == LG_EMPTY || prev == key) return s;
+        s = (s + 1) & t.mask;
+    }
+}
+__device__ __forceinline__ int km_find(const KeyTable &t, unsigned long long key) {
+    unsigned int s = hash64(key) & t.mask;
+    while (true) {
+        const unsigned long long cur = t.keys[s];
+        if (cur == key) return (int)s;
+        if (cur == LG_EMPTY) return -1;
+        s = (s + 1) & t.mask;
+    }
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(256) k_km_first(const IdT *__restrict__ ids, long long npx, int merge, KeyTable t, int *status) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long key;
+        if (!km_key(ids, i, merge, &key, status)) continue;
+        atomicMin(t.first + km_insert(t, key), (unsigned long long)i);
+    }
+}
+template <typename IdT>
+__global__ void __launch_bounds__(256) k_km_first_mask(const IdT *__restrict__ ids, long long npx, int merge, KeyTable t,
+                                                        unsigned char *__restrict__ mask, int *status) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long key;
+        unsigned char m = 0;
+        if (km_key(ids, i, merge, &key, status)) {
+            const int s = km_find(t, key);
+            m = (s >= 0 && t.first[s] == (unsigned long long)i) ? 1 : 0;
+        }
+        mask[i] = m;
+    }
+}
+template <typename IdT>
+__global__ void __launch_bounds__(256) k_km_seed(const IdT *__restrict__ ids, const long long *__restrict__ seeds, long long n_seeds,
+                                                  long long npx, int merge, KeyTable t, int *status) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_seeds; j += (long long)gridDim.x * blockDim.x) {
+        const long long i = seeds[j];
+        if (i < 0 || i >= npx) { atomicOr(status, 2); continue; }
+        unsigned long long key;
+        if (km_key(ids, i, merge, &key, status)) km_insert(t, key);
+    }
+}
+template <typename IdT>
+__global__ void __launch_bounds__(256) k_km_drop(IdT *__restrict__ ids, long long npx, int merge, KeyTable t, int *status) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long key;
+        if (!km_key(ids, i, merge, &key, status)) continue;
+        if (km_find(t, key) >= 0) {
+            IdT z;
+            z.x = 0; z.y = 0; z.z = 0; z.w = 0;
+            ids[i] = z;
+        }
+    }
+}
+
+static long long km_capacity(long long n) {
+    long long cap = 64;
+    while (cap < 2 * n + 2) cap <<= 1;
+    return cap;
+}
+extern "C" int64_t srx_corrmap_keys_workspace_bytes(int64_t n_keys_upper_bound) {
+    if (n_keys_upper_bound < 0 || n_keys_upper_bound > (1ll << 30)) return -1;
+    return km_capacity(n_keys_upper_bound) * 16 + 256;
+}
+
+static int km_setup(KeyTable *t, int **status, void *ws, int64_t ws_bytes, long long n, cudaStream_t st) {
+    const long long cap = km_capacity(n);
+    SRX_REQUIRE(ws && ws_bytes >= cap * 16 + 256, SRX_ERR_INVALID, "workspace too small");
+    t->keys = reinterpret_cast<unsigned long long *>(ws);
+    t->first = t->keys + cap;
+    t->mask = (unsigned int)(cap - 1);
+    *status = reinterpret_cast<int *>(t->first + cap);
+    SRX_CUDA_CHECK(cudaMemsetAsync(ws, 0xFF, (size_t)cap * 16, st));   // keys = EMPTY, first = max
+    SRX_CUDA_CHECK(cudaMemsetAsync(*status, 0, 256, st));
+    return SRX_OK;
+}
+static int km_finish(int *status, cudaStream_t st) {
+    int h = 0;
+    SRX_CUDA_CHECK(cudaGetLastError());
+    SRX_CUDA_CHECK(cudaMemcpyAsync(&h, status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SRX_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h & 2) return srx_set_error(SRX_ERR_INDEX, "seed pixel index out of range");
+    if (h & 1) return srx_set_error(SRX_ERR_KEY_RANGE, "an id tuple does not fit the exact 64-bit key (sprite, material < 1024, third component < 4096)");
+    return SRX_OK;
+}
+static int km_grid(long long n) {
+    const long long nb = (n + 255) / 256, cap = (long long)srx_sm_count_cached() * 8;
+    return (int)(nb < 1 ? 1 : (nb < cap ? nb : cap));
+}
+
+// mask_out[i] = 1 where pixel i (frame, row, col order) is the first one carrying its key: the keys of the reference's dict
+// in insertion order are the keys of the marked pixels in index order (correspondence_map.py:148-168).  Syncs.
+extern "C" int srx_corrmap_first_appearance(const void *ids_dev, int id_dtype, int frames, int height, int width, int merge_len,
+                                            uint8_t *mask_out_dev, void *workspace_dev, int64_t workspace_bytes, void *stream) {
+    SRX_REQUIRE(ids_dev && mask_out_dev, SRX_ERR_INVALID, "null argument");
+    SRX_REQUIRE(frames > 0 && height > 0 && width > 0, SRX_ERR_INVALID, "non-positive dimension");
+    SRX_REQUIRE(id_dtype == SRX_I32 || id_dtype == SRX_I16, SRX_ERR_INVALID, "id dtype must be int32 or int16");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long npx = (long long)frames * height * width;
+    const int merge = merge_len > 1 ? merge_len : 1;
+    KeyTable t;
+    int *status;
+    int rc = km_setup(&t, &status, workspace_dev, workspace_bytes, npx, st);
+    if (rc) return rc;
+    if (id_dtype == SRX_I32) {
+        k_km_first<int4><<<km_grid(npx), 256, 0, st>>>(reinterpret_cast<const int4 *>(ids_dev), npx, merge, t, status);
+        k_km_first_mask<int4><<<km_grid(npx), 256, 0, st>>>(reinterpret_cast<const int4 *>(ids_dev), npx, merge, t, mask_out_dev, status);
+    } else {
+        k_km_first<short4><<<km_grid(npx), 256, 0, st>>>(reinterpret_cast<const short4 *>(ids_dev), npx, merge, t, status);
+        k_km_first_mask<short4><<<km_grid(npx), 256, 0, st>>>(reinterpret_cast<const short4 *>(ids_dev), npx, merge, t, mask_out_dev, status);
+    }
+    return km_finish(status, st);
+}
+
+// Clears the ids of every pixel whose key equals the key of one of the seed pixels (linear indices into [F,H,W]) — deleting
+// keys from the reference's dict (correspondence_map.py:219-223, 268-274).  In place.  Syncs.
+extern "C" int srx_corrmap_drop_keys(void *ids_dev, int id_dtype, int frames, int height, int width, int merge_len,
+                                     const int64_t *seed_pixels_dev, int64_t n_seeds, void *workspace_dev, int64_t workspace_bytes,
+                                     void *stream) {
+    SRX_REQUIRE(ids_dev, SRX_ERR_INVALID, "null argument");
+    SRX_REQUIRE(frames > 0 && height > 0 && width > 0 && n_seeds >= 0, SRX_ERR_INVALID, "bad sizes");
+    SRX_REQUIRE(id_dtype == SRX_I32 || id_dtype == SRX_I16, SRX_ERR_INVALID, "id dtype must be int32 or int16");
+    if (n_seeds == 0) return SRX_OK;
+    SRX_REQUIRE(seed_pixels_dev, SRX_ERR_INVALID, "null seed list");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long npx = (long long)frames * height * width;
+    const int merge = merge_len > 1 ? merge_len : 1;
+    KeyTable t;
+    int *status;
+    int rc = km_setup(&t, &status, workspace_dev, workspace_bytes, n_seeds, st);
+    if (rc) return rc;
+    const long long *seeds = reinterpret_cast<const long long *>(seed_pixels_dev);
+    if (id_dtype == SRX_I32) {
+        k_km_seed<int4><<<km_grid(n_seeds), 256, 0, st>>>(reinterpret_cast<const int4 *>(ids_dev), seeds, n_seeds, npx, merge, t, status);
+        k_km_drop<int4><<<km_grid(npx), 256, 0, st>>>(reinterpret_cast<int4 *>(ids_dev), npx, merge, t, status);
+    } else {
+        k_km_seed<short4><<<km_grid(n_seeds), 256, 0, st>>>(reinterpret_cast<const short4 *>(ids_dev), seeds, n_seeds, npx, merge, t, status);
+        k_km_drop<short4><<<km_grid(npx), 256, 0, st>>>(reinterpret_cast<short4 *>(ids_dev), npx, merge, t, status);
+    }
+    return km_finish(status, st);
+}

@@ -66,6 +66,104 @@ class CorrespondenceMap:
         if d > 1:
             self._merge_len = max(self._merge_len, 1) * d
 
+    # -- dropouts and cache (correspondence_map.py:177-274) ----------------------------------------------------------------
+    def _device(self) -> torch.device:
+        if self._ids.is_cuda:
+            return self._ids.device
+        from .. import _lib
+        if not torch.cuda.is_available():
+            raise _lib.SrxUnavailable("CorrespondenceMap maintenance runs on the GPU (there is no CPU path)")
+        self._ids = self._ids.cuda()
+        self._device_ids = {}
+        return self._ids.device
+
+    def _first_appearance(self) -> torch.Tensor:
+        """Linear pixel indices (frame, row, col order) that introduce a key: the reference dict's keys in insertion order."""
+        import ctypes as C
+        from .. import _lib
+        dev = self._device()
+        lib = _lib.load()
+        F, H, W = self.num_frames, self.height, self.width
+        npx = F * H * W
+        mask = torch.empty(npx, dtype=torch.uint8, device=dev)
+        ws = torch.empty(int(lib.srx_corrmap_keys_workspace_bytes(npx)), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.srx_corrmap_first_appearance(self._ids.data_ptr(), _lib.torch_dtype_code(self._ids.dtype), F, H, W,
+                                                        self._merge_len, mask.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                        _lib.current_stream_ptr(dev)))
+        return torch.nonzero(mask).flatten()
+
+    def _drop(self, seeds: torch.Tensor) -> None:
+        import ctypes as C
+        from .. import _lib
+        dev = self._device()
+        lib = _lib.load()
+        seeds = seeds.to(device=dev, dtype=torch.int64).contiguous()
+        n = int(seeds.numel())
+        if n == 0:
+            return
+        ws = torch.empty(int(lib.srx_corrmap_keys_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.srx_corrmap_drop_keys(self._ids.data_ptr(), _lib.torch_dtype_code(self._ids.dtype), self.num_frames,
+                                                 self.height, self.width, self._merge_len, seeds.data_ptr(), n, ws.data_ptr(),
+                                                 ws.numel(), _lib.current_stream_ptr(dev)))
+        self._device_ids = {}
+
+    def dropout_index(self, probability: float, seed: int):
+        """`dropout_index` (correspondence_map.py:207-223): every key is deleted with `probability`; the decisions come from
+        Python's `random` seeded with `seed`, one draw per key in the dict's insertion order — replayed here over the
+        first-appearance order of the keys.  Irreversible, like the reference."""
+        import random
+        assert 0 <= probability <= 1
+        first = self._first_appearance()
+        random.seed(seed)
+        flags = [random.random() < probability for _ in range(int(first.numel()))]
+        self._drop(first[torch.tensor(flags, dtype=torch.bool, device=first.device)] if flags else first[:0])
+
+    def dropout_in_rectangle(self, rectangle, at_frame: int):
+        """`dropout_in_rectangle` (correspondence_map.py:225-274): deletes every key that has a pixel strictly inside the
+        rectangle `((r0, c0), (r1, c1))` (or an object with `.top_left` / `.bottom_right`) at frame `at_frame`."""
+        assert 0 <= at_frame <= self.num_frames
+        if isinstance(rectangle, tuple):
+            top_left, bottom_right = rectangle
+        elif hasattr(rectangle, "top_left") and hasattr(rectangle, "bottom_right"):
+            top_left, bottom_right = rectangle.top_left, rectangle.bottom_right
+        else:
+            raise ValueError(f"Data type of {type(rectangle)} is not supported for rectangle")
+        assert self.width >= max(top_left[0], bottom_right[0])
+        assert self.height >= max(top_left[1], bottom_right[1])
+        if at_frame >= self.num_frames:
+            return
+        dev = self._device()
+        rows = torch.arange(max(top_left[0] + 1, 0), min(bottom_right[0], self.height), device=dev, dtype=torch.int64)
+        cols = torch.arange(max(top_left[1] + 1, 0), min(bottom_right[1], self.width), device=dev, dtype=torch.int64)
+        if rows.numel() == 0 or cols.numel() == 0:
+            return
+        seeds = (at_frame * self.height + rows.view(-1, 1)) * self.width + cols.view(1, -1)
+        self._drop(seeds.reshape(-1))
+
+    def save_cache(self, path: str):
+        """`save_cache` (correspondence_map.py:194-205): pickles the map ('<dir>/corr_map.pkl' when a directory is given)."""
+        import pickle
+        path = str(path)
+        if os.path.exists(path) and os.path.isdir(path):
+            path = os.path.join(path, "corr_map.pkl")
+        with open(path, "wb") as f:
+            pickle.dump({"ids": self._ids.cpu(), "merge_len": self._merge_len}, f)
+
+    @classmethod
+    def LoadFromCache(cls, path: str) -> "CorrespondenceMap":
+        """`LoadFromCache` (correspondence_map.py:177-192)."""
+        import pickle
+        path = str(path)
+        if os.path.exists(path) and os.path.isdir(path):
+            path = os.path.join(path, "corr_map.pkl")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"Correspondence map cache file not found at {path}")
+        with open(path, "rb") as f:
+            d = pickle.load(f)
+        return cls(d["ids"], merge_len=d["merge_len"])
+
     # -- construction ---------------------------------------------------------------------------------------------------
     @classmethod
     def from_ids(cls, ids: torch.Tensor, num_frames: Optional[int] = None, merge_len: int = 0) -> "CorrespondenceMap":
