@@ -193,6 +193,17 @@ def legacy_cases(R):
     save("legacy_resize_overlap", ids=ids.numpy(), frames=torch.stack(frames).numpy(), view_normal=vn.numpy(),
          alpha=np.float64(0.7), **res)
 
+    # build_view_normal_map (overlap/utils.py:56-102): PIL normal images, [1,3] and [3] view vectors
+    from PIL import Image
+    rng = np.random.default_rng(4)
+    imgs = rng.integers(0, 256, size=(3, 8, 10, 3), dtype=np.uint8)
+    pil = [Image.fromarray(a, mode="RGB") for a in imgs]
+    v13 = torch.tensor([[0.3, -0.5, 0.8]])
+    v3 = torch.tensor([0.3, -0.5, 0.8])
+    vn13 = R["overlap_utils"].build_view_normal_map(pil, v13).numpy()
+    vn3 = R["overlap_utils"].build_view_normal_map(pil, v3).numpy()
+    save("legacy_view_normal", images=imgs, v13=v13.numpy(), v3=v3.numpy(), out13=vn13, out3=vn3)
+
     # scheduler table (overlap_scheduler.py:89-107 / utils.py:24-53); cosine only works for tensor timesteps
     rows = []
     for itype in ("constant", "linear", "exponential", "cosine"):

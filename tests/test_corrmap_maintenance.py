@@ -66,3 +66,19 @@ def test_gpu_dropouts_match_reference(golden, tag, merge, id_dtype):
     assert len(z) == len(_keys(O.correspondence_traces(c["ids"], merge)))
     z.dropout_index(1.0, 1)
     assert len(z) == 0 and not z.ids.any()
+
+
+@pytest.mark.parametrize("tag", ["13", "3"])
+def test_build_view_normal_map_matches_reference(golden, tag):
+    """`build_view_normal_map` (overlap/utils.py:56-102) for a [1,3] view vector (normalised per component by the reference's
+    `F.normalize(dim=0)`) and a [3] vector (normalised to unit length): oracle and host helper against the reference's output."""
+    from PIL import Image
+    from stable_renderer_b200.overlap import build_view_normal_map
+    g = golden("legacy_view_normal")
+    o = O.build_view_normal_map(g["images"].astype(np.float32) / 255.0, g["v" + tag])
+    assert np.array_equal(o, g["out" + tag])
+    pil = [Image.fromarray(a, mode="RGB") for a in g["images"]]
+    got = build_view_normal_map(pil, torch.from_numpy(g["v" + tag])).numpy()
+    assert got.shape == g["out" + tag].shape and np.array_equal(got, g["out" + tag])
+    with pytest.raises(TypeError):
+        build_view_normal_map(tuple(pil), torch.from_numpy(g["v" + tag]))
