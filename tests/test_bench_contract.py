@@ -1,0 +1,52 @@
+"""The JSON line `bench.py` prints (the driver depends on it): reference arm on CPU, our arm on a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COMMON = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+          "dtype", "data", "config", "e2e")
+
+
+def _line(args, timeout):
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, timeout=timeout)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, proc.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = _line(["--impl", "reference", "--steps", "3", "--warmup", "3"], 600)
+    for k in COMMON:
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "overlap_latent_px_per_sec" and d["unit"] == "latent-px/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.gpu
+def test_our_arm_line():
+    d = _line(["--steps", "60", "--warmup", "3"], 900)
+    for k in COMMON + ("clocks", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "overlap_latent_px_per_sec" and d["n_gpus"] == 1 and d["steps"] == 60 and d["warmup"] == 3
+    assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("cfg2") and "l2" in d["config"]
+    assert d["gpu_launches"] >= d["steps"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] < 1
+    assert r["traffic"] is None or r["traffic"] >= r["bytes_per_launch"] * 0.9
+    e = d["e2e"]
+    assert e["value"] > 0 and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] < d["value"]                      # host copies are inside the timed region
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and 0 < cb["value"] < d["value"]
+    c = d["clocks"]
+    assert set(c) >= {"sm_mhz", "sm_max_mhz", "reasons"}
