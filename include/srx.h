@@ -249,6 +249,19 @@ int srx_corrmap_first_appearance(const void *ids_dev, int id_dtype, int frames, 
 int srx_corrmap_drop_keys(void *ids_dev, int id_dtype, int frames, int height, int width, int merge_len,
                           const int64_t *seed_pixels_dev, int64_t n_seeds, void *workspace_dev, int64_t workspace_bytes, void *stream);
 
+/* CorrMapLatentNoiseInitializer (legacy_codes/nodes/latent.py:10-40): keys with >= 2 entries ("traces") get one random
+ * 4-vector for the latent and one for the noise, drawn in dict insertion order (:28-35), then a nearest down-sample (:37-38).
+ *   srx_corrmap_trace_ranks: rank_out[i] = index of pixel i's key among the traces in insertion order, -1 otherwise;
+ *       *n_traces_out (host) = number of traces.  Syncs.
+ *   srx_corrmap_noise_fill: base [2,4,H,W] (latent base, noise base: one frame each, repeated over the batch, :22-26),
+ *       rows [n_traces,2,4] (latent row, noise row) -> latent_out / noise_out [batch,4,lat_h,lat_w], evaluated only at the
+ *       pixels the down-sample keeps.  batch < frames is an error (IndexError in the reference). */
+int64_t srx_corrmap_trace_ranks_workspace_bytes(int64_t n_pixels);
+int srx_corrmap_trace_ranks(const void *ids_dev, int id_dtype, int frames, int height, int width, int merge_len,
+                            int32_t *rank_out_dev, int64_t *n_traces_out, void *workspace_dev, int64_t workspace_bytes, void *stream);
+int srx_corrmap_noise_fill(const int32_t *rank_dev, int frames, int height, int width, int batch, int lat_h, int lat_w,
+                           const float *base_dev, const float *rows_dev, float *latent_out_dev, float *noise_out_dev, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Bake — replaces CorrespondMap.update/_update (source/engine/static/corrmap.py:578-736)
  * ------------------------------------------------------------------------------------------------------------------ */
@@ -311,6 +324,54 @@ int srx_tensor_to_array(void *cuda_array, const void *src_dev, int width, int he
 /* test helpers: plain cudaArray allocation so that the copy kernels can be exercised without a GL context */
 int srx_array_alloc(void **cuda_array_out, int width, int height, int channels, int bits_per_channel, int kind /*0 sint,1 uint,2 float*/);
 int srx_array_free(void *cuda_array);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * G-buffer frame ingest — replaces RenderManager._save_frame_data (source/engine/managers/renderManager.py:877-948) and the
+ * "closer pixel wins" merge of identical-G-buffer draws (renderManager.py:121-133).  Attachments are linear device buffers in
+ * the layout of Texture.tensor() (texture.py:166-254): colour / normal+depth / noise RGBA16F, ids RGBA_32I, position / canny
+ * RGB32F (renderManager.py:206-367); flip_rows = the buffers are still in GL row order (origin bottom-left).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct srx_gbuffer {
+    const void *color;         /* [H,W,4] fp16; alpha = coverage */
+    const void *ids;           /* [H,W,4] int32 (spriteID, materialID, map_index, vertexID) */
+    const float *pos;          /* [H,W,3] f32 */
+    const void *normal_depth;  /* [H,W,4] fp16: normal*0.5+0.5, reversed depth */
+    const void *noise;         /* [H,W,4] fp16 */
+    const void *canny;         /* [H,W,3] fp16 (the reference's tensor dtype: data_type HALF, renderManager.py:353) or f32 */
+    int canny_dtype;           /* SRX_F16 | SRX_F32; canny_maps has the same dtype */
+} srx_gbuffer;
+
+typedef struct srx_ingest_args {
+    srx_gbuffer src;           /* color is required; the others may be NULL when their outputs are NULL */
+    int height, width;         /* multiples of 8 */
+    int flip_rows;
+    int64_t frame_slot;        /* which frame of the batch tensors below this frame becomes */
+    const float *bg_noise;     /* [H,W,4] f32 RenderManager.GlobalBGNoise (:869-875), top-left origin */
+    void *color_maps;          /* fp16 [F,H,W,3] (:884)            any output may be NULL = not wanted */
+    void *masks;               /* fp16 [F,H,W] = 1 - alpha (:883) */
+    int32_t *id_maps;          /* [F,H,W,4] (:895) */
+    float *pos_maps;           /* [F,H,W,3] (:902) */
+    void *normal_maps;         /* fp16 [F,H,W,3] (:910) */
+    void *depth_maps;          /* fp16 [F,H,W,3]: depth repeated three times (:911-912) */
+    void *canny_maps;          /* [F,H,W,3] in the attachment's dtype (:942) */
+    float *noise_maps;         /* f32 [F,4,H/8,W/8] (:925-937): mask mix, mean of 64 consecutive pixels, AdaIN vs the raw attachment */
+    void *workspace;           /* srx_ingest_workspace_bytes(height, width), 256-byte aligned; needed when noise_maps != NULL */
+    int64_t workspace_bytes;
+} srx_ingest_args;
+int64_t srx_ingest_workspace_bytes(int height, int width);
+int srx_frame_ingest(const srx_ingest_args *args, void *stream);
+
+typedef struct srx_gbuffer_temp {   /* RenderManager._*_buffer_temp (renderManager.py:219-357), top-left origin; NULL = not kept */
+    void *color;               /* fp16 [H,W,4] */
+    int32_t *ids;              /* [H,W,4] */
+    float *pos;                /* [H,W,3] */
+    void *normal;              /* fp16 [H,W,3] */
+    void *depth;               /* fp16 [H,W] (required) */
+    void *noise;               /* fp16 [H,W,4] */
+    void *canny;               /* fp16 [H,W,3] */
+} srx_gbuffer_temp;
+/* Where cur's reversed depth > temp->depth, every attachment of the pixel replaces the stored one (in place). */
+int srx_gbuffer_merge_closer(const srx_gbuffer *cur, int height, int width, int flip_rows, const srx_gbuffer_temp *temp, void *stream);
 
 #ifdef __cplusplus
 }

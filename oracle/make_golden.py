@@ -299,7 +299,135 @@ def dump_cases(R):
          loaded_values=m2._values.numpy().view(np.uint16), loaded_writtens=m2._writtens.numpy(), meta=np.array(meta))
 
 
+def latent_init_cases(R):
+    """The legacy node CorrMapLatentNoiseInitializer.__call__ (legacy_codes/nodes/latent.py:10-40), the real class, on the
+    `legacy_corrmap` id buffers: full map and merge_nearby(4); square 8x down-sample, a non-integer ratio, batch > frames."""
+    CorrespondenceMap = R["correspondence_map"].CorrespondenceMap
+    Node = R["legacy_latent_node"].CorrMapLatentNoiseInitializer
+    T, H, W = 4, 32, 32
+    ids = synthetic.make_ids(T, H, W, tex_h=16, tex_w=16, seed=31, legacy_layout=True, dtype=torch.int16)
+    with tempfile.TemporaryDirectory() as td:
+        iddir = os.path.join(td, "id")
+        os.makedirs(iddir)
+        for f in range(T):
+            np.save(os.path.join(iddir, f"id_{f}.npy"), ids[f].numpy())
+        with ref_shim.quiet():
+            cmap = CorrespondenceMap.FromExisting(iddir, enable_cache=False)
+    merged = CorrespondenceMap(dict(cmap.Map), cmap.width, cmap.height, cmap.num_frames)
+    with ref_shim.quiet():
+        merged.merge_nearby(4)
+    out = {}
+    cases = []
+    for tag, cm in (("full", cmap), ("merge4", merged)):
+        for (width, height, batch, seed) in ((256, 256, 4, 7), (80, 48, 6, 123456789), (64, 64, 4, 0)):
+            with ref_shim.quiet():
+                (d,) = Node()(width, height, batch, seed, cm)
+            name = f"{tag}_{width}x{height}_b{batch}_s{seed}"
+            out[name + "_samples"] = d["samples"].numpy()
+            out[name + "_noise"] = d["noise"].numpy()
+            cases.append((tag, width, height, batch, seed))
+        out[tag + "_n_traces"] = np.int64(sum(1 for v in cm.Map.values() if len(v) > 1))
+    save("legacy_latent_init", ids=ids.numpy(), cases=np.array([f"{t}:{w}:{h}:{b}:{s}" for t, w, h, b, s in cases]), **out)
+
+
+def _gbuffer_attachments(g, H, W, coverage):
+    """Synthetic attachments in GL row order (origin bottom-left), dtypes of renderManager.py:206-367."""
+    alpha = (torch.rand(H, W, generator=g) < coverage).float()
+    edge = torch.rand(H, W, generator=g) < 0.1
+    alpha = torch.where(edge, torch.rand(H, W, generator=g), alpha)              # anti-aliased edges: fractional coverage
+    color = torch.cat([torch.rand(H, W, 3, generator=g), alpha.unsqueeze(-1)], dim=-1).half()
+    ids = torch.randint(0, 5000, (H, W, 4), generator=g, dtype=torch.int32) * (alpha > 0).int().unsqueeze(-1)
+    pos = torch.randn(H, W, 3, generator=g)
+    nd = torch.cat([torch.rand(H, W, 3, generator=g), (torch.rand(H, W, 1, generator=g) * (alpha > 0).float().unsqueeze(-1))], dim=-1).half()
+    noise = (torch.randn(H, W, 4, generator=g) * 1.3 + 0.2).half()
+    canny = torch.rand(H, W, 3, generator=g).half()        # cannyFBOTex is read as a HALF tensor (renderManager.py:353)
+    return dict(color=color, ids=ids, pos=pos, normal_depth=nd, noise=noise, canny=canny)
+
+
+def ingest_cases(R):
+    """RenderManager._save_frame_data (renderManager.py:877-948) and the closer-pixel merge (:121-133).  RenderManager cannot
+    be imported (OpenGL, window, managers), so the two bodies are replayed statement by statement on CPU tensors around the
+    reference's REAL adaptive_instance_normalization; `Texture.tensor(update=True, flip=True)` becomes `.flip(0)` of the
+    GL-order attachment (texture.py:236,253)."""
+    ain = R["math_utils"].adaptive_instance_normalization
+    g = torch.Generator().manual_seed(2024)
+    H, W = 48, 64
+    bg = torch.randn((1, H, W, 4), generator=g, dtype=torch.float32)
+    data = {}
+    src_all = []
+    for frame in range(2):
+        src = _gbuffer_attachments(g, H, W, 0.55)
+        src_all.append(src)
+        tex = {k: v.flip(0) for k, v in src.items()}                                          # Texture.tensor(flip=True)
+
+        def cat(key, val):
+            data[key] = val if key not in data else torch.cat([data[key], val], dim=0)
+        color_data = tex["color"].clone().unsqueeze(0)
+        mask_data = 1.0 - color_data[..., 3].squeeze(-1)
+        color_data = color_data[..., :3]
+        cat("color_maps", color_data)
+        cat("masks", mask_data)
+        cat("id_maps", tex["ids"].clone().unsqueeze(0))
+        cat("pos_maps", tex["pos"].clone().unsqueeze(0))
+        nd = tex["normal_depth"].clone().unsqueeze(0)
+        normal_data = nd[..., :3]
+        depth_data = nd[..., 3].unsqueeze(-1)
+        depth_data = torch.cat([depth_data, ] * 3, dim=-1)
+        cat("normal_maps", normal_data)
+        cat("depth_maps", depth_data)
+        noise = tex["noise"].clone().unsqueeze(0)
+        mask = mask_data.unsqueeze(-1).expand_as(noise).to(device=noise.device)
+        noise = noise * (1.0 - mask) + bg * mask
+        height, width = noise.shape[1], noise.shape[2]
+        noise = noise.view(-1, 8, 8, 4).mean(dim=(1, 2)).view(height // 8, width // 8, 4)
+        noise = ain(noise.unsqueeze(0), tex["noise"].unsqueeze(0), mode='NHWC')
+        noise = noise.contiguous()
+        cat("noise_maps", noise)
+        cat("canny_maps", tex["canny"].clone().unsqueeze(0))
+    out = {"bg_noise": bg.numpy()}
+    for f, src in enumerate(src_all):
+        for k, v in src.items():
+            out[f"src{f}_{k}"] = v.numpy().view(np.uint16) if v.dtype == torch.float16 else v.numpy()
+    for k, v in data.items():
+        out[k] = v.numpy().view(np.uint16) if v.dtype == torch.float16 else v.numpy()
+
+    # closer-pixel merge of three draws (renderManager.py:121-133 with the buffers of :219-357)
+    temp = dict(color=torch.zeros(H, W, 4, dtype=torch.float16), ids=torch.zeros(H, W, 4, dtype=torch.int32),
+                pos=torch.zeros(H, W, 3), normal=torch.zeros(H, W, 3, dtype=torch.float16),
+                depth=torch.zeros(H, W, dtype=torch.float16), noise=torch.zeros(H, W, 4, dtype=torch.float16),
+                canny=torch.zeros(H, W, 3, dtype=torch.float16))
+    for d in range(3):
+        src = _gbuffer_attachments(g, H, W, 0.4)
+        if d == 2:
+            src["normal_depth"][..., 3] = src_prev["normal_depth"][..., 3]                  # equal depths: the earlier draw stays
+        src_prev = src
+        for k, v in src.items():
+            out[f"draw{d}_{k}"] = v.numpy().view(np.uint16) if v.dtype == torch.float16 else v.numpy()
+        cur = src["normal_depth"].flip(0)
+        current_depth = cur[..., -1].squeeze()
+        current_normal = cur[..., :-1]
+        closer = current_depth > temp["depth"]
+        temp["depth"][closer] = current_depth[closer]
+        temp["normal"][closer] = current_normal[closer]
+        temp["color"][closer] = src["color"].flip(0)[closer]
+        temp["ids"][closer] = src["ids"].flip(0)[closer]
+        temp["pos"][closer] = src["pos"].flip(0)[closer]
+        temp["noise"][closer] = src["noise"].flip(0)[closer]
+        temp["canny"][closer] = src["canny"].flip(0)[closer]
+    for k, v in temp.items():
+        out[f"temp_{k}"] = v.numpy().view(np.uint16) if v.dtype == torch.float16 else v.numpy()
+    save("frame_ingest", **out)
+
+
 def main():
+    if "--only-ingest" in sys.argv:
+        torch.set_num_threads(1)
+        ingest_cases(ref_shim.load_reference())
+        return
+    if "--only-latent-init" in sys.argv:
+        torch.set_num_threads(1)
+        latent_init_cases(ref_shim.load_reference())
+        return
     if not ref_shim.available():
         raise SystemExit("reference tree not mounted; fixtures can only be regenerated in the build container")
     torch.set_num_threads(1)
@@ -310,6 +438,8 @@ def main():
     step_cases(R)
     bake_cases(R)
     legacy_cases(R)
+    latent_init_cases(R)
+    ingest_cases(R)
 
 
 if __name__ == "__main__":

@@ -234,6 +234,14 @@ def load_reference() -> dict:
                                      "legacy_codes/stable_rendering_algo/overlap/overlap_scheduler.py", "legacy_algo.overlap")
     out["overlap"] = _load("legacy_algo.overlap.overlap",
                            "legacy_codes/stable_rendering_algo/overlap/overlap.py", "legacy_algo.overlap")
+    # legacy node CorrMapLatentNoiseInitializer: needs only three names of the ComfyUI type system
+    _stub("comfyUI")
+    _stub("comfyUI.types", StableRenderingNode=type("StableRenderingNode", (), {}), INT=lambda *a, **k: int, LATENT=dict, torch=None)
+    del sys.modules["comfyUI.types"].__dict__["torch"]
+    _stub("stable_rendering")
+    _stub("stable_rendering.src")
+    _stub("stable_rendering.src.data_classes", CorrespondenceMap=out["correspondence_map"].CorrespondenceMap)
+    out["legacy_latent_node"] = _load("legacy_nodes.latent", "legacy_codes/nodes/latent.py")
     _LOADED = out
     return out
 

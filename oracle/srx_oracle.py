@@ -604,3 +604,95 @@ def traces_dropout_in_rectangle(traces: Dict[tuple, list], rectangle, at_frame: 
                 del out[key]
                 break
     return out
+
+
+# =====================================================================================================
+# L8 (legacy): CorrMapLatentNoiseInitializer (legacy_codes/nodes/latent.py:10-40)
+# =====================================================================================================
+def corrmap_latent_noise_init(traces: Dict[tuple, list], map_width: int, map_height: int, width: int, height: int,
+                              batch_size: int, base_latent: np.ndarray, base_noise: np.ndarray,
+                              rows: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Arithmetic of the node given its random numbers: ``base_*`` ``[4,Hm,Wm]`` are the two base draws (:22,25, repeated
+    over the batch), ``rows`` ``[n_traces,2,4]`` the per-trace (latent, noise) draws in dict order, singleton keys skipped
+    (:28-35); then F.interpolate(mode='nearest') to (height // 8, width // 8) (:37-38).  Returns (samples, noise)."""
+    latent = np.repeat(np.asarray(base_latent, dtype=np.float32)[None], batch_size, axis=0)
+    noise = np.repeat(np.asarray(base_noise, dtype=np.float32)[None], batch_size, axis=0)
+    assert latent.shape == (batch_size, 4, map_height, map_width)
+    n = 0
+    for trace in traces.values():
+        if len(trace) == 1:
+            continue
+        for (r, c, f) in trace:
+            latent[f, :, r, c] = rows[n, 0]
+            noise[f, :, r, c] = rows[n, 1]
+        n += 1
+    assert n == len(rows)
+    sy = nearest_resize_index(height // 8, map_height)
+    sx = nearest_resize_index(width // 8, map_width)
+    return latent[:, :, sy][:, :, :, sx], noise[:, :, sy][:, :, :, sx]
+
+
+def corrmap_latent_noise_draws(seed: int, map_width: int, map_height: int, n_traces: int):
+    """The node's random stream, call for call (:18-35): both manual_seed calls return the same default generator, so the
+    effective seed is ``seed + 1``; then the two base draws and 2 x ``randn(4)`` per trace."""
+    import torch
+    torch.manual_seed(seed)
+    torch.manual_seed(seed + 1)
+    base_latent = torch.randn([1, 4, map_height, map_width])[0].numpy()
+    base_noise = torch.randn([1, 4, map_height, map_width])[0].numpy()
+    rows = np.zeros((n_traces, 2, 4), dtype=np.float32)
+    for i in range(n_traces):
+        rows[i, 0] = torch.randn(4).numpy()
+        rows[i, 1] = torch.randn(4).numpy()
+    return base_latent, base_noise, rows
+
+
+# =====================================================================================================
+# §8f-2: frame ingest (source/engine/managers/renderManager.py:877-948) and closer-pixel merge (:121-133)
+# =====================================================================================================
+def _h(a) -> np.ndarray:
+    return np.asarray(a, dtype=np.float32).astype(np.float16)
+
+
+def frame_ingest(color: np.ndarray, ids: np.ndarray, pos: np.ndarray, normal_depth: np.ndarray, noise: np.ndarray,
+                 canny: np.ndarray, bg_noise: np.ndarray, flip: bool = True) -> Dict[str, np.ndarray]:
+    """One frame of ``_save_frame_data``.  Inputs are the attachments ``[H,W,C]`` (fp16 colour / normal+depth / noise,
+    int32 ids, f32 position, canny in its own dtype) in GL row order when ``flip``; ``bg_noise`` ``[H,W,4]`` f32.
+    Every fp16 operation rounds where torch rounds it: mask (:883), ``1 - mask`` and ``noise * (1 - mask)`` (:929);
+    the 64-consecutive-pixel mean of the NHWC view (:933); AdaIN with fp16 style statistics (math_utils.py:39-51)."""
+    f = (lambda a: np.asarray(a)[::-1]) if flip else (lambda a: np.asarray(a))
+    color, ids, pos, nd, noise, canny = f(color), f(ids), f(pos), f(normal_depth), f(noise), f(canny)
+    H, W = color.shape[:2]
+    mask = _h(np.float32(1.0) - color[..., 3].astype(np.float32))
+    out = {"color_maps": color[..., :3].copy(), "masks": mask, "id_maps": ids.copy(), "pos_maps": pos.copy(),
+           "normal_maps": nd[..., :3].copy(), "depth_maps": np.repeat(nd[..., 3:4], 3, axis=-1), "canny_maps": canny.copy()}
+    m32 = mask.astype(np.float32)[..., None]
+    one_minus = _h(np.float32(1.0) - m32)
+    prod = _h(noise.astype(np.float32) * one_minus.astype(np.float32))
+    mixed = prod.astype(np.float32) + np.asarray(bg_noise, dtype=np.float32).reshape(H, W, 4) * m32
+    pooled = mixed.reshape(-1, 64, 4).astype(np.float64).mean(axis=1)                       # [H*W/64, 4]
+    n = pooled.shape[0]
+    c_mean = pooled.mean(axis=0).astype(np.float32)
+    c_std = np.sqrt(pooled.var(axis=0, ddof=1).astype(np.float32) + np.float32(1e-5))
+    s = noise.reshape(-1, 4).astype(np.float64)
+    s_var = _h(s.var(axis=0, ddof=1))
+    s_std = _h(np.sqrt(_h(s_var.astype(np.float32) + np.float32(1e-5)).astype(np.float32)))
+    s_mean = _h(s.mean(axis=0))
+    norm = (pooled.astype(np.float32) - c_mean) / c_std
+    res = norm * s_std.astype(np.float32) + s_mean.astype(np.float32)
+    out["noise_maps"] = np.ascontiguousarray(res.astype(np.float32).T).reshape(4, H // 8, W // 8)
+    return out
+
+
+def gbuffer_merge_closer(temp: Dict[str, np.ndarray], color, ids, pos, normal_depth, noise, canny, flip: bool = True) -> None:
+    """One draw of the identical-G-buffer merge, in place on ``temp`` (keys color/ids/pos/normal/depth/noise/canny)."""
+    f = (lambda a: np.asarray(a)[::-1]) if flip else (lambda a: np.asarray(a))
+    nd = f(normal_depth)
+    closer = nd[..., 3].astype(np.float32) > temp["depth"].astype(np.float32)
+    temp["depth"][closer] = nd[..., 3][closer]
+    temp["normal"][closer] = nd[..., :3][closer]
+    temp["color"][closer] = f(color)[closer]
+    temp["ids"][closer] = f(ids)[closer]
+    temp["pos"][closer] = f(pos)[closer]
+    temp["noise"][closer] = f(noise)[closer]
+    temp["canny"][closer] = f(canny)[closer].astype(np.float16)

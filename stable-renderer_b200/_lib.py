@@ -73,6 +73,23 @@ class srx_bake_args(C.Structure):
                 ("normal_depth_dev", C.c_void_p), ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_int64), ("phase", C.c_int)]
 
 
+class srx_gbuffer(C.Structure):
+    _fields_ = [("color", C.c_void_p), ("ids", C.c_void_p), ("pos", C.c_void_p), ("normal_depth", C.c_void_p),
+                ("noise", C.c_void_p), ("canny", C.c_void_p), ("canny_dtype", C.c_int)]
+
+
+class srx_ingest_args(C.Structure):
+    _fields_ = [("src", srx_gbuffer), ("height", C.c_int), ("width", C.c_int), ("flip_rows", C.c_int), ("frame_slot", C.c_int64),
+                ("bg_noise", C.c_void_p), ("color_maps", C.c_void_p), ("masks", C.c_void_p), ("id_maps", C.c_void_p),
+                ("pos_maps", C.c_void_p), ("normal_maps", C.c_void_p), ("depth_maps", C.c_void_p), ("canny_maps", C.c_void_p),
+                ("noise_maps", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
+class srx_gbuffer_temp(C.Structure):
+    _fields_ = [("color", C.c_void_p), ("ids", C.c_void_p), ("pos", C.c_void_p), ("normal", C.c_void_p), ("depth", C.c_void_p),
+                ("noise", C.c_void_p), ("canny", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol of include/srx.h is listed (tests check the export table against it)
 _PROTOTYPES = {
     "srx_version": (C.c_int, []),
@@ -87,6 +104,11 @@ _PROTOTYPES = {
                                                C.c_int64, C.c_void_p]),
     "srx_corrmap_drop_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                         C.c_int64, C.c_void_p]),
+    "srx_corrmap_trace_ranks_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "srx_corrmap_trace_ranks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
+                                          C.c_void_p, C.c_int64, C.c_void_p]),
+    "srx_corrmap_noise_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "srx_atlas_quantize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "srx_atlas_dequantize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "srx_group_rank_workspace_ints": (C.c_int64, [C.c_int64]),
@@ -122,6 +144,9 @@ _PROTOTYPES = {
                                       C.c_void_p]),
     "srx_array_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "srx_array_free": (C.c_int, [C.c_void_p]),
+    "srx_ingest_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "srx_frame_ingest": (C.c_int, [C.POINTER(srx_ingest_args), C.c_void_p]),
+    "srx_gbuffer_merge_closer": (C.c_int, [C.POINTER(srx_gbuffer), C.c_int, C.c_int, C.c_int, C.POINTER(srx_gbuffer_temp), C.c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -33,6 +33,9 @@ int srx_set_error(int code, const char *fmt, ...);
     } while (0)
 
 int srx_sm_count_cached();
+// srx_group.cu: in-place exclusive scan of a 0/1 int array (entry -> rank among the set entries, -1 where clear)
+long long srx_flags_scan_scratch_ints(long long n);
+int srx_flags_to_ranks(int *flags, long long n, int *scratch, int64_t *total, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------------
 // device helpers

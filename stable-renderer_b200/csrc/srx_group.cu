@@ -142,6 +142,15 @@ static int gr_rank_table(int *table, long long kcap, int *scratch /* ntiles + 2 
     return SRX_OK;
 }
 
+// In-place exclusive scan of a 0/1 int array for other translation units (srx_legacy.cu): entry -> its rank among the set
+// entries, -1 where clear.  scratch: srx_flags_scan_scratch_ints(n) ints.  Syncs.
+long long srx_flags_scan_scratch_ints(long long n) { return (n + GR_TILE - 1) / GR_TILE + 4; }
+int srx_flags_to_ranks(int *flags, long long n, int *scratch, int64_t *total, cudaStream_t st) {
+    const int ntiles = (int)((n + GR_TILE - 1) / GR_TILE);
+    SRX_CUDA_CHECK(cudaMemsetAsync(scratch + ntiles, 0, 4 * sizeof(int), st));
+    return gr_rank_table(flags, n, scratch, total, scratch + ntiles + 1, st);
+}
+
 extern "C" int64_t srx_group_rank_workspace_ints(int64_t key_capacity) {
     return key_capacity + (key_capacity + GR_TILE - 1) / GR_TILE + 4;
 }

@@ -487,3 +487,133 @@ extern "C" int srx_corrmap_drop_keys(void *ids_dev, int id_dtype, int frames, in
     }
     return km_finish(status, st);
 }
+
+// =================================================================================================================
+// CorrMapLatentNoiseInitializer (legacy_codes/nodes/latent.py:26-40): every key with at least two entries ("trace") gets
+// one random 4-vector for the latent and one for the noise, drawn in the dict's insertion order; all its pixels receive
+// them; then a nearest down-sample.  The random rows are drawn by the caller (the reference's CPU generator stream);
+// here: which row belongs to which pixel (rank of the pixel's key among the traces, in insertion order) and the fill of
+// exactly the pixels the down-sample keeps.
+// =================================================================================================================
+template <typename IdT>
+__global__ void __launch_bounds__(256) k_km_first_count(const IdT *__restrict__ ids, long long npx, int merge, KeyTable t,
+                                                         unsigned int *__restrict__ count, int *status) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long key;
+        if (!km_key(ids, i, merge, &key, status)) continue;
+        const unsigned int s = km_insert(t, key);
+        atomicMin(t.first + s, (unsigned long long)i);
+        atomicAdd(count + s, 1u);
+    }
+}
+template <typename IdT>
+__global__ void __launch_bounds__(256) k_km_trace_flag(const IdT *__restrict__ ids, long long npx, int merge, KeyTable t,
+                                                        const unsigned int *__restrict__ count, int *__restrict__ flag, int *status) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long key;
+        int f = 0;
+        if (km_key(ids, i, merge, &key, status)) {
+            const int s = km_find(t, key);
+            f = (s >= 0 && t.first[s] == (unsigned long long)i && count[s] >= 2u) ? 1 : 0;   // latent.py:29-30 skips singletons
+        }
+        flag[i] = f;
+    }
+}
+// rank[i] <- rank of the pixel that introduced i's key.  In place: an introducing pixel rewrites its own value, the
+// others read only introducing pixels.
+template <typename IdT>
+__global__ void __launch_bounds__(256) k_km_trace_rank(const IdT *__restrict__ ids, long long npx, int merge, KeyTable t,
+                                                        int *rank, int *status) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long key;
+        if (!km_key(ids, i, merge, &key, status)) continue;
+        const int s = km_find(t, key);
+        if (s < 0) continue;
+        const long long f = (long long)t.first[s];
+        if (f != i) rank[i] = rank[f];
+    }
+}
+
+extern "C" int64_t srx_corrmap_trace_ranks_workspace_bytes(int64_t n_pixels) {
+    if (n_pixels < 0 || n_pixels > (1ll << 30)) return -1;
+    return km_capacity(n_pixels) * 20 + 256 + lg_align(srx_flags_scan_scratch_ints(n_pixels) * 4);
+}
+
+// rank_out[i] = index of pixel i's key among the keys with >= 2 entries, in dict insertion order; -1 for pixels without an
+// id and for single-entry keys.  *n_traces_out (host) = number of such keys.  Syncs.
+extern "C" int srx_corrmap_trace_ranks(const void *ids_dev, int id_dtype, int frames, int height, int width, int merge_len,
+                                       int32_t *rank_out_dev, int64_t *n_traces_out, void *workspace_dev, int64_t workspace_bytes,
+                                       void *stream) {
+    SRX_REQUIRE(ids_dev && rank_out_dev && n_traces_out, SRX_ERR_INVALID, "null argument");
+    SRX_REQUIRE(frames > 0 && height > 0 && width > 0, SRX_ERR_INVALID, "non-positive dimension");
+    SRX_REQUIRE(id_dtype == SRX_I32 || id_dtype == SRX_I16, SRX_ERR_INVALID, "id dtype must be int32 or int16");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long npx = (long long)frames * height * width;
+    SRX_REQUIRE(npx <= (1ll << 30), SRX_ERR_INVALID, "too many pixels");
+    SRX_REQUIRE(workspace_dev && workspace_bytes >= srx_corrmap_trace_ranks_workspace_bytes(npx), SRX_ERR_INVALID, "workspace too small");
+    SRX_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 255) == 0, SRX_ERR_INVALID, "workspace must be 256-byte aligned");
+    const int merge = merge_len > 1 ? merge_len : 1;
+    const long long cap = km_capacity(npx);
+    KeyTable t;
+    int *status;
+    int rc = km_setup(&t, &status, workspace_dev, cap * 16 + 256, npx, st);   // keys, first, status
+    if (rc) return rc;
+    unsigned char *after = reinterpret_cast<unsigned char *>(status) + 256;
+    unsigned int *count = reinterpret_cast<unsigned int *>(after);
+    int *scratch = reinterpret_cast<int *>(after + cap * 4);
+    SRX_CUDA_CHECK(cudaMemsetAsync(count, 0, (size_t)cap * 4, st));
+    const int grid = km_grid(npx);
+    if (id_dtype == SRX_I32) {
+        const int4 *ids = reinterpret_cast<const int4 *>(ids_dev);
+        k_km_first_count<int4><<<grid, 256, 0, st>>>(ids, npx, merge, t, count, status);
+        k_km_trace_flag<int4><<<grid, 256, 0, st>>>(ids, npx, merge, t, count, rank_out_dev, status);
+    } else {
+        const short4 *ids = reinterpret_cast<const short4 *>(ids_dev);
+        k_km_first_count<short4><<<grid, 256, 0, st>>>(ids, npx, merge, t, count, status);
+        k_km_trace_flag<short4><<<grid, 256, 0, st>>>(ids, npx, merge, t, count, rank_out_dev, status);
+    }
+    rc = srx_flags_to_ranks(rank_out_dev, npx, scratch, n_traces_out, st);
+    if (rc) return rc;
+    if (id_dtype == SRX_I32)
+        k_km_trace_rank<int4><<<grid, 256, 0, st>>>(reinterpret_cast<const int4 *>(ids_dev), npx, merge, t, rank_out_dev, status);
+    else
+        k_km_trace_rank<short4><<<grid, 256, 0, st>>>(reinterpret_cast<const short4 *>(ids_dev), npx, merge, t, rank_out_dev, status);
+    return km_finish(status, st);
+}
+
+// out[b,c,y,x] = rows[rank, which, c] when frame b's pixel sampled by F.interpolate(mode="nearest") (latent.py:37-38)
+// belongs to a trace, else base[which, c, sy, sx] (the same base frame repeats over the batch, latent.py:22-26).
+__global__ void __launch_bounds__(256) k_corrmap_noise_fill(const int *__restrict__ rank, const float *__restrict__ base,
+                                                             const float *__restrict__ rows, float *__restrict__ latent_out,
+                                                             float *__restrict__ noise_out, int frames, int H, int W, int batch,
+                                                             int h, int w, float scale_y, float scale_x) {
+    const long long total = (long long)batch * h * w;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(o % w), y = (int)((o / w) % h), b = (int)(o / ((long long)w * h));
+        int sy = (int)floorf(__fmul_rn((float)y, scale_y)), sx = (int)floorf(__fmul_rn((float)x, scale_x));
+        sy = sy < H - 1 ? sy : H - 1;
+        sx = sx < W - 1 ? sx : W - 1;
+        const long long src = (long long)sy * W + sx;
+        const int r = b < frames ? rank[(long long)b * H * W + src] : -1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const long long dst = (((long long)b * 4 + c) * h + y) * w + x;
+            latent_out[dst] = r >= 0 ? rows[(long long)r * 8 + c] : base[(long long)c * H * W + src];
+            noise_out[dst] = r >= 0 ? rows[(long long)r * 8 + 4 + c] : base[((long long)4 + c) * H * W + src];
+        }
+    }
+}
+
+extern "C" int srx_corrmap_noise_fill(const int32_t *rank_dev, int frames, int height, int width, int batch, int lat_h, int lat_w,
+                                      const float *base_dev, const float *rows_dev, float *latent_out_dev, float *noise_out_dev,
+                                      void *stream) {
+    SRX_REQUIRE(rank_dev && base_dev && latent_out_dev && noise_out_dev, SRX_ERR_INVALID, "null argument");
+    SRX_REQUIRE(frames > 0 && height > 0 && width > 0 && batch > 0 && lat_h > 0 && lat_w > 0, SRX_ERR_INVALID, "non-positive dimension");
+    SRX_REQUIRE(batch >= frames, SRX_ERR_INDEX, "batch_size %d is smaller than the map's %d frames (IndexError in latent.py:34)", batch, frames);
+    const long long total = (long long)batch * lat_h * lat_w;
+    const volatile float sy = (float)height / (float)lat_h, sx = (float)width / (float)lat_w;
+    k_corrmap_noise_fill<<<km_grid(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        rank_dev, base_dev, rows_dev, latent_out_dev, noise_out_dev, frames, height, width, batch, lat_h, lat_w, sy, sx);
+    SRX_CUDA_CHECK(cudaGetLastError());
+    return SRX_OK;
+}
