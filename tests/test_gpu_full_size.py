@@ -1,0 +1,114 @@
+"""-m gpu parity at BASELINE.json's full sizes (configs 3 and 5: 96 x 1024^2 ids / 128x128x4 latents, 768 x 512^2 ids / 64x64x4
+latents), where the numpy oracle would take minutes: size-independent properties of the overlap step, and an independent
+restatement of the reference's op chain (corresponder.py:298-376) in torch CUDA ops with float64 accumulation and an explicit
+last-writer per cell (the order the reference's one-thread `index_put_` has)."""
+import pytest
+import torch
+
+from helpers import assert_close, t2n
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 3e-6
+CONFIGS = {"cfg3": (96, 1024, 128, 1024), "cfg5": (768, 512, 64, 512)}     # frames, id size, latent size, texture size
+
+
+def _torch_chain(ids: torch.Tensor, x: torch.Tensor, ratio: float) -> torch.Tensor:
+    """Reference op chain on the GPU, one frame block at a time for the index arithmetic, float64 sums."""
+    F, H, W, _ = ids.shape
+    B, C, h, w = x.shape
+    x64 = x.double()
+    K = int(ids[..., 3].max().item()) + 1
+    sums = torch.zeros(K, C, dtype=torch.float64, device=x.device)
+    cnts = torch.zeros(K, dtype=torch.float64, device=x.device)
+    winner = torch.full((B * h * w,), -1, dtype=torch.int64, device=x.device)     # packed (pixel order, key) of the last valid pixel
+    cells, keys = [], []
+    for f in range(F):
+        idf = ids[f]
+        keep = (idf[..., 2] != 2048) & (idf != 0).any(dim=-1)                     # corrmap.py:266-275
+        yy, xx = keep.nonzero(as_tuple=True)
+        key = idf[yy, xx, 3].to(torch.float32).long()                              # the key goes through float32 (corrmap.py:256-261)
+        sx = ((xx.float() / H) * w).long()                                         # corresponder.py:312-313 with corrmap.py:239,249
+        sy = ((yy.float() / W) * h).long()
+        cell = (f * h + sy) * w + sx
+        vals = x64[f][:, sy, sx].t()                                               # [n, C]
+        sums.index_add_(0, key, vals)
+        cnts.index_add_(0, key, torch.ones_like(key, dtype=torch.float64))
+        order = yy * W + xx                                                        # entry order inside the frame
+        winner.scatter_reduce_(0, cell, order * K + key, reduce="amax")
+    mean = (sums / cnts.clamp(min=1).unsqueeze(1)).float()                         # reference sums and divides in float32
+    has = winner >= 0
+    wkey = (winner % K).clamp(min=0)
+    flat = x.float().permute(0, 2, 3, 1).reshape(-1, C)                            # [B*h*w, C]
+    blended = torch.where(has.unsqueeze(1), (1 - ratio) * flat + ratio * mean[wkey], flat)
+    b = blended.reshape(B, h, w, C).permute(0, 3, 1, 2).reshape(B, C, -1).double()
+    c = x64.reshape(B, C, -1)
+    c_mean, c_std = c.mean(2, keepdim=True), (c.var(2, keepdim=True) + 1e-5).sqrt()
+    s_mean, s_std = b.mean(2, keepdim=True), (b.var(2, keepdim=True) + 1e-5).sqrt()
+    return ((c - c_mean) / c_std * s_std + s_mean).reshape(B, C, h, w)
+
+
+def _make(cfg):
+    from stable_renderer_b200 import synthetic
+    F, H, h, tex = CONFIGS[cfg]
+    ids = synthetic.make_ids(F, H, H, tex_h=tex, tex_w=tex, frac_2048=0.05, seed=1234 + F, device="cuda")
+    x0 = synthetic.make_latents(F, 4, h, h, seed=0, device="cuda")
+    return ids, x0, tex * tex
+
+
+@pytest.mark.parametrize("cfg", ["cfg3", "cfg5"])
+def test_full_size_step_properties(cfg):
+    from stable_renderer_b200.plan import OverlapPlan
+    ids, x0, cap = _make(cfg)
+    F = ids.shape[0]
+    plan = OverlapPlan(ids, x0.shape, key_capacity=cap)
+    assert plan.fused
+
+    # (1) against the torch restatement of the reference's op chain at full size
+    x = x0.clone()
+    plan.step(x, 0.5)
+    plan.check()
+    want = _torch_chain(ids, x0, 0.5)
+    assert_close(t2n(x), t2n(want), RTOL, ATOL, cfg + " vs torch chain")
+
+    # (2) inject ratio 0: the blended tensor is x itself, so AdaIN returns x
+    y = x0.clone()
+    plan.step(y, 0.0)
+    assert_close(t2n(y), t2n(x0), RTOL, ATOL, cfg + " ratio 0")
+
+    # (3) the split kernels (another implementation of the same step) agree at full size
+    z = x0.clone()
+    split = OverlapPlan(ids, x0.shape, key_capacity=cap, split_kernels=True)
+    assert not split.fused
+    split.step(z, 0.5)
+    split.check()
+    assert_close(t2n(z), t2n(x), RTOL, ATOL, cfg + " split vs fused")
+
+    # (4) cached-plan regime from the bucketing pass
+    c = x0.clone()
+    plan.build_cache()
+    plan.step(c, 0.5, cached=True)
+    plan.check()
+    assert_close(t2n(c), t2n(x), RTOL, ATOL, cfg + " cached vs streaming")
+
+    # (5) frame-permutation equivariance: frames are independent except through the key means, which are sums over all frames
+    perm = torch.randperm(F, generator=torch.Generator().manual_seed(3)).cuda()
+    p = x0[perm].contiguous()
+    OverlapPlan(ids[perm].contiguous(), x0.shape, key_capacity=cap).step(p, 0.5)
+    assert_close(t2n(p), t2n(x[perm]), RTOL, ATOL, cfg + " frame permutation")
+
+    # (6) scaling the latents by 2 scales the result by 2 (exact in floating point except for the +1e-5 under the root)
+    s = (x0 * 2).contiguous()
+    plan.step(s, 0.5)
+    assert_close(t2n(s), t2n(x) * 2, 2e-5, 1e-5, cfg + " scaling")
+
+
+def test_full_size_step_bf16_cfg3():
+    """config 3's dtype: bf16 latents, tolerance 1e-2 (north_star)."""
+    from stable_renderer_b200.plan import OverlapPlan
+    ids, x0, cap = _make("cfg3")
+    xb = x0.to(torch.bfloat16)
+    want = _torch_chain(ids, xb.float(), 0.5)
+    plan = OverlapPlan(ids, xb.shape, key_capacity=cap)
+    plan.step(xb, 0.5)
+    plan.check()
+    assert_close(t2n(xb), t2n(want), 1e-2, 1e-2, "cfg3 bf16")
