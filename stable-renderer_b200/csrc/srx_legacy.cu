@@ -29,7 +29,15 @@ struct LegacyGeom {
     int strategy;
     int resize;     // 1: ResizeOverlap (apply where()), 0: Overlap at id resolution
     unsigned int mask;  // table capacity - 1
+    float up_sy, up_sx;      // fl32(h / H), fl32(w / W): id pixel -> latent cell (F.interpolate up-sample, overlap.py:205-206)
+    float down_sy, down_sx;  // fl32(H / h), fl32(W / w): latent cell -> sampled id pixel (down-sample, overlap.py:217-218)
 };
+
+// F.interpolate(mode='nearest') source index: min(floor(dst * fl32(in/out)), in-1)
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+    const int s = (int)floorf(__fmul_rn((float)dst, scale));
+    return s < in_size - 1 ? s : in_size - 1;
+}
 
 __device__ __forceinline__ int floordiv(int a, int b) {
     int q = a / b;
@@ -72,7 +80,6 @@ struct LegacyBufs {
     float *wsum;               // [ncell]
     float *cnt;                // [ncell]  L
     float *wself;              // [ncell]  w_i (view-normal)
-    int *up_y, *up_x, *down_y, *down_x;
     int *status;
 };
 
@@ -84,9 +91,9 @@ __global__ void __launch_bounds__(256) k_legacy_seed(const IdT *__restrict__ ids
         const long long t = cell / g.w;
         const int sy = (int)(t % g.h);
         const int f = (int)(t / g.h);
-        const int py = b.down_y[sy], px = b.down_x[sx];
+        const int py = nearest_src(sy, g.down_sy, g.H), px = nearest_src(sx, g.down_sx, g.W);
         const long long pix = ((long long)f * g.H + py) * g.W + px;
-        const int uy = b.up_y[py], ux = b.up_x[px];
+        const int uy = nearest_src(py, g.up_sy, g.h), ux = nearest_src(px, g.up_sx, g.w);
         for (int c = 0; c < g.C; ++c)
             b.selfx[cell * g.C + c] = XIo<XT>::ld(x + (((long long)f * g.C + c) * g.h + uy) * g.w + ux);
         const IdPx p = load_id(ids + pix);
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(256) k_legacy_accum(const IdT *__restrict__ id
         const long long t = j / g.W;
         const int yj = (int)(t % g.H);
         const int fj = (int)(t / g.H);
-        const XT *xp = x + (((long long)fj * g.C) * g.h + b.up_y[yj]) * g.w + b.up_x[xj];
+        const XT *xp = x + (((long long)fj * g.C) * g.h + nearest_src(yj, g.up_sy, g.h)) * g.w + nearest_src(xj, g.up_sx, g.w);
         const long long plane = (long long)g.h * g.w;
         float wj = 1.f;
         if (g.strategy == SRX_STRATEGY_VIEW_NORMAL) wj = vn_weight(vnmap[j]);
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(256) k_legacy_accum(const IdT *__restrict__ id
                 wgt = __fdiv_rn(1.f, (float)(abs(fi - fj) + 1));                   // algorithms.py:66-70
             } else if (g.strategy == SRX_STRATEGY_PIXEL_DISTANCE) {
                 const int r = i % (g.h * g.w);
-                const int yi = b.down_y[r / g.w], xi = b.down_x[r % g.w];
+                const int yi = nearest_src(r / g.w, g.down_sy, g.H), xi = nearest_src(r % g.w, g.down_sx, g.W);
                 wgt = __fdiv_rn(1.f, (float)(abs(xi - xj) + abs(yi - yj) + 1));    // algorithms.py:87-93
             }
             float *dst = b.sum + (long long)i * g.C;
@@ -189,8 +196,8 @@ __global__ void __launch_bounds__(256) k_legacy_finalize(XT *__restrict__ x, Leg
 // ---- host ---------------------------------------------------------------------------------------------------------------
 struct LegacyLayout {
     int64_t cap, ncell;
-    int64_t keys, head, next, cellslot, selfx, sum, wsum, cnt, wself, tables, status, total;
-    int64_t zero_begin, zero_end;  // [sum .. cnt] cleared per call
+    int64_t keys, head, next, cellslot, selfx, sum, wsum, cnt, wself, status, total;
+    int64_t zero_begin, zero_end;  // [sum .. cnt, status] cleared per call; [keys .. head] set to 0xFF per call
 };
 
 static inline int64_t lg_align(int64_t v) { return (v + 255) / 256 * 256; }
@@ -211,10 +218,9 @@ static LegacyLayout legacy_layout(const srx_legacy_desc *d) {
     L.sum = off; off = lg_align(off + L.ncell * d->channels * 4);
     L.wsum = off; off = lg_align(off + L.ncell * 4);
     L.cnt = off; off = lg_align(off + L.ncell * 4);
+    L.status = off; off += 256;
     L.zero_end = off;
     L.wself = off; off = lg_align(off + L.ncell * 4);
-    L.tables = off; off = lg_align(off + (int64_t)(d->height + d->width + d->lat_h + d->lat_w) * 4);
-    L.status = off; off += 256;
     L.total = off;
     return L;
 }
@@ -233,14 +239,9 @@ extern "C" int64_t srx_legacy_workspace_bytes(const srx_legacy_desc *d) {
     return legacy_layout(d).total;
 }
 
-// F.interpolate(mode='nearest') source index: min(floor(dst * fl32(in/out)), in-1)
-static void nearest_table(int *dst, int out_size, int in_size) {
-    volatile float scale = (float)in_size / (float)out_size;
-    for (int i = 0; i < out_size; ++i) {
-        volatile float v = (float)i * scale;
-        int s = (int)floorf(v);
-        dst[i] = s < in_size - 1 ? s : in_size - 1;
-    }
+static float nearest_scale(int in_size, int out_size) {
+    volatile float s = (float)in_size / (float)out_size;   // one float32 division, as torch computes the scale
+    return s;
 }
 
 template <typename IdT, typename XT>
@@ -257,22 +258,10 @@ static int legacy_impl(const srx_legacy_desc *d, const srx_legacy_args *a, cudaS
     b.wsum = reinterpret_cast<float *>(ws + L.wsum);
     b.cnt = reinterpret_cast<float *>(ws + L.cnt);
     b.wself = reinterpret_cast<float *>(ws + L.wself);
-    b.up_y = reinterpret_cast<int *>(ws + L.tables);
-    b.up_x = b.up_y + d->height;
-    b.down_y = b.up_x + d->width;
-    b.down_x = b.down_y + d->lat_h;
     b.status = reinterpret_cast<int *>(ws + L.status);
 
-    std::vector<int> tab((size_t)d->height + d->width + d->lat_h + d->lat_w);
-    nearest_table(tab.data(), d->height, d->lat_h);                                   // up: id row -> latent row
-    nearest_table(tab.data() + d->height, d->width, d->lat_w);
-    nearest_table(tab.data() + d->height + d->width, d->lat_h, d->height);            // down: latent row -> id row
-    nearest_table(tab.data() + d->height + d->width + d->lat_h, d->lat_w, d->width);
-    SRX_CUDA_CHECK(cudaMemcpyAsync(b.up_y, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    SRX_CUDA_CHECK(cudaMemsetAsync(b.keys, 0xFF, (size_t)L.cap * 8, st));
-    SRX_CUDA_CHECK(cudaMemsetAsync(b.head, 0xFF, (size_t)L.cap * 4, st));
-    SRX_CUDA_CHECK(cudaMemsetAsync(ws + L.zero_begin, 0, (size_t)(L.zero_end - L.zero_begin), st));
-    SRX_CUDA_CHECK(cudaMemsetAsync(b.status, 0, 256, st));
+    SRX_CUDA_CHECK(cudaMemsetAsync(b.keys, 0xFF, (size_t)(L.next - L.keys), st));                       // keys = EMPTY, head = -1
+    SRX_CUDA_CHECK(cudaMemsetAsync(ws + L.zero_begin, 0, (size_t)(L.zero_end - L.zero_begin), st));    // sums, counts, status
 
     LegacyGeom g;
     g.T = d->frames; g.H = d->height; g.W = d->width; g.h = d->lat_h; g.w = d->lat_w; g.C = d->channels;
@@ -280,6 +269,8 @@ static int legacy_impl(const srx_legacy_desc *d, const srx_legacy_args *a, cudaS
     g.strategy = d->strategy;
     g.resize = (d->lat_h != d->height || d->lat_w != d->width) ? 1 : 0;
     g.mask = (unsigned int)(L.cap - 1);
+    g.up_sy = nearest_scale(d->lat_h, d->height); g.up_sx = nearest_scale(d->lat_w, d->width);
+    g.down_sy = nearest_scale(d->height, d->lat_h); g.down_sx = nearest_scale(d->width, d->lat_w);
     const int sms = srx_sm_count_cached();
     const long long npx = (long long)d->frames * d->height * d->width;
     const IdT *ids = reinterpret_cast<const IdT *>(a->ids_dev);
@@ -291,7 +282,7 @@ static int legacy_impl(const srx_legacy_desc *d, const srx_legacy_args *a, cudaS
     SRX_CUDA_CHECK(cudaGetLastError());
     int st_host = 0;
     SRX_CUDA_CHECK(cudaMemcpyAsync(&st_host, b.status, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SRX_CUDA_CHECK(cudaStreamSynchronize(st));  // also keeps `tab` alive until the upload has been consumed
+    SRX_CUDA_CHECK(cudaStreamSynchronize(st));
     if (st_host)
         return srx_set_error(SRX_ERR_KEY_RANGE, "an id component does not fit the packed 64-bit key "
                              "(int32 ids: sprite, material < 1024, third component < 4096 after merge, fourth >= 0)");

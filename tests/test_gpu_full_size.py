@@ -21,7 +21,6 @@ def _torch_chain(ids: torch.Tensor, x: torch.Tensor, ratio: float) -> torch.Tens
     sums = torch.zeros(K, C, dtype=torch.float64, device=x.device)
     cnts = torch.zeros(K, dtype=torch.float64, device=x.device)
     winner = torch.full((B * h * w,), -1, dtype=torch.int64, device=x.device)     # packed (pixel order, key) of the last valid pixel
-    cells, keys = [], []
     for f in range(F):
         idf = ids[f]
         keep = (idf[..., 2] != 2048) & (idf != 0).any(dim=-1)                     # corrmap.py:266-275
@@ -112,3 +111,57 @@ def test_full_size_step_bf16_cfg3():
     plan.step(xb, 0.5)
     plan.check()
     assert_close(t2n(xb), t2n(want), 1e-2, 1e-2, "cfg3 bf16")
+
+
+def _torch_bake(colors, ids, mode, k2, texels, prior_written=None):
+    """CorrespondMap.update semantics (corrmap.py:672-736, ignore_obj_mat_id / no masks) with the last writer made explicit:
+    `replace` = last pixel of the last frame that shows the texel; `first` = last pixel of the EARLIEST frame that shows it,
+    among texels not written before the call.  Returns (values fp16 [k2*texels,4], written bool)."""
+    F, H, W, _ = ids.shape
+    n = k2 * texels
+    dev = ids.device
+    texel = (ids[..., 2].long() * texels + ids[..., 3].long()).reshape(-1)
+    pix = torch.arange(H * W, device=dev).repeat(F)
+    frame = torch.arange(F, device=dev).repeat_interleave(H * W)
+    rank = (frame if mode == "replace" else (F - 1 - frame)) * (H * W) + pix
+    owner = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    owner.scatter_reduce_(0, texel, rank, reduce="amax")
+    written = owner >= 0
+    if prior_written is not None and mode == "first":
+        written &= ~prior_written
+    own = owner.clamp(min=0)
+    src_frame = own // (H * W)
+    if mode == "first":
+        src_frame = F - 1 - src_frame
+    src = src_frame * (H * W) + own % (H * W)
+    rgb = colors.reshape(-1, colors.shape[-1])[src]
+    rgba = torch.cat([rgb, torch.ones_like(rgb[:, :1])], dim=1).half()                 # alpha appended (corrmap.py:681-684)
+    values = torch.where(written.unsqueeze(1), rgba, torch.zeros_like(rgba))
+    return values, written
+
+
+@pytest.mark.parametrize("mode", ["replace", "first"])
+def test_full_size_bake_cfg4_bit_exact(mode):
+    """config 4: 64 views 1024^2 (RGB f32) into a 4096^2 fp16 RGBA atlas, bit for bit; then a second `first` call keeps it."""
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import CorrespondMap
+    V, H, tex = 64, 1024, 4096
+    ids = synthetic.make_ids(V, H, H, tex_h=tex, tex_w=tex, k=1, frac_2048=0.0, seed=99, device="cuda")
+    keep = (ids != 0).any(dim=-1)
+    colors = torch.rand(V, H, H, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    masks = (~keep).float()                                                               # IDMap.masks: 1 = no id
+    cm = CorrespondMap(name="t", k=1, height=tex, width=tex, channel_count=4, device="cuda")
+    cm.update(colors, ids, mode=mode, masks=masks, inverse_masks=True, ignore_obj_mat_id=True)
+    # pixels without an id are masked out: give them a texel outside the atlas for the restatement by dropping them
+    ids_kept = ids.clone()
+    ids_kept[..., 2][~keep] = 0
+    flat_tex = torch.where(keep, ids[..., 3], torch.full_like(ids[..., 3], tex * tex))   # dump slot for masked pixels
+    ids_kept[..., 3] = flat_tex
+    values, written = _torch_bake(colors, ids_kept, mode, 1, tex * tex + 1)
+    values, written = values[:-1], written[:-1]
+    assert torch.equal(cm._writtens.reshape(-1).bool(), written)
+    assert torch.equal(cm._values.reshape(-1, 4).view(torch.int16), values.view(torch.int16))
+    if mode == "first":
+        before = cm._values.clone()
+        cm.update(colors.flip(0), ids.flip(0), mode="first", masks=masks.flip(0), inverse_masks=True, ignore_obj_mat_id=True)
+        assert torch.equal(cm._values, before)                                            # every texel of these views is already written
