@@ -335,7 +335,11 @@ class CorrespondMap:
             if sharded:
                 a.phase = 1
                 _lib.check(lib.srx_bake_update(C.byref(a), stream))
-                dist.all_reduce(self._workspace[:need - 256].view(torch.float32), op=dist.ReduceOp.SUM, group=process_group)
+                ntex = self.k * self.k * self.height * self.width
+                # RGB into an RGBA atlas: the weight sums live in the accumulator's alpha channel (csrc/srx_bake.cu), the
+                # separate [ntex] weight array stays zero and is not exchanged
+                nbytes = ntex * 16 if (self.channel_count == 4 and colors.shape[-1] == 3) else need - 256
+                dist.all_reduce(self._workspace[:nbytes].view(torch.float32), op=dist.ReduceOp.SUM, group=process_group)
                 a.phase = 2
                 _lib.check(lib.srx_bake_update(C.byref(a), stream))
             else:

@@ -9,7 +9,8 @@
 //             EARLIEST frame that touches the texel.
 // Both are "max over an order key", so all frames are processed in parallel:
 //   B1 claim : owner[texel] = atomicMax(order(frame, pixel) + 1)          ids (+mask) streamed once
-//   B2 write : the pixel whose order equals owner[texel] converts its colour to fp16 and stores it
+//   B2 write : the pixel whose order equals owner[texel] converts its colour to fp16 and stores it — pushed by the pixels
+//              (small updates) or pulled by the texels through the owner word (k_bake_write_texels)
 // The weighted multi-view bake (not in the reference) replaces B1/B2 with a vector-atomic
 // weighted sum per texel and a per-texel finalize.
 #include "srx_common.cuh"
@@ -93,6 +94,34 @@ __global__ void __launch_bounds__(256) k_bake_write(const IdT *__restrict__ ids,
     }
 }
 
+// B2, texel-major: the owner word names the winning pixel, so the atlas can pull instead of the pixels pushing — one
+// pass over the owner words, a colour gather for claimed texels only; the ids are not read a second time and the colours of
+// losing pixels are never read.  Used when the views hold at least half as many pixels as the atlas has texels.
+template <typename CT>
+__global__ void __launch_bounds__(256) k_bake_write_texels(const CT *__restrict__ colors, uint8_t *__restrict__ writtens,
+                                                            const unsigned int *__restrict__ owner, __half *__restrict__ values,
+                                                            BakeGeom g, long long ntex) {
+    const long long hw = (long long)g.H * g.W;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntex; t += (long long)gridDim.x * blockDim.x) {
+        const unsigned int o = __ldcs(owner + t);
+        if (o == 0u) continue;
+        const long long order = (long long)o - 1;
+        const long long fo = order / hw, pix = order - fo * hw;
+        const long long i = (g.first_mode ? (g.frames_total - 1 - fo) : fo) * hw + pix;
+        const CT *c = colors + i * g.Cin;
+        __half *v = values + t * g.C;
+        if (g.C == 4) {
+            __half h4[4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) h4[ch] = __float2half_rn(ch < g.Cin ? color_ld<CT>(c + ch) : 1.f);
+            *reinterpret_cast<uint2 *>(v) = *reinterpret_cast<const uint2 *>(h4);
+        } else {
+            for (int ch = 0; ch < g.C; ++ch) v[ch] = __float2half_rn(ch < g.Cin ? color_ld<CT>(c + ch) : 1.f);
+        }
+        writtens[t] = 1;
+    }
+}
+
 // ---- weighted multi-view bake -----------------------------------------------------------------------------------
 __device__ __forceinline__ float bake_weight(const __half *__restrict__ nd, long long i, int mode) {
     if (mode == SRX_WEIGHT_UNIFORM || nd == nullptr) return 1.f;
@@ -117,15 +146,17 @@ __global__ void __launch_bounds__(256) k_bake_accum(const IdT *__restrict__ ids,
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) v[ch] = ch < g.C ? __fmul_rn(w, ch < g.Cin ? color_ld<CT>(c + ch) : 1.f) : 0.f;
         red_add_f32x4(acc + tex * 4, v[0], v[1], v[2], v[3]);
-        red_add_f32(wsum + tex, w);
+        // RGB colours into an RGBA atlas: the appended alpha is 1 (corrmap.py:681-684), so channel 3 accumulates w * 1 — the
+        // weight sum itself; the separate scalar reduction (half of all L2 atomics, which bound this kernel) is not needed
+        if (!(g.C == 4 && g.Cin == 3)) red_add_f32(wsum + tex, w);
     }
 }
 
 __global__ void __launch_bounds__(256) k_bake_finalize(const float *__restrict__ acc, const float *__restrict__ wsum,
                                                         __half *__restrict__ values, uint8_t *__restrict__ writtens,
-                                                        long long ntex, int C, int first_mode) {
+                                                        long long ntex, int C, int first_mode, int w_in_alpha) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntex; t += (long long)gridDim.x * blockDim.x) {
-        const float w = wsum[t];
+        const float w = w_in_alpha ? acc[t * 4 + 3] : wsum[t];
         if (!(w > 0.f)) continue;
         if (first_mode && writtens[t]) continue;
         for (int ch = 0; ch < C; ++ch) values[t * C + ch] = __float2half_rn(__fdiv_rn(acc[t * 4 + ch], w));
@@ -176,8 +207,14 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
             const float *masks = a->masks_dev ? a->masks_dev + (long long)f0 * hw : nullptr;
             SRX_CUDA_CHECK(cudaMemsetAsync(owner, 0, (size_t)ntex * 4, st));
             k_bake_claim<IdT><<<grid, 256, 0, st>>>(ids + (long long)f0 * hw, masks, a->writtens_dev, owner, status, g, npx);
-            k_bake_write<IdT, CT><<<grid, 256, 0, st>>>(ids + (long long)f0 * hw, masks, colors + (long long)f0 * hw * g.Cin,
-                                                        a->writtens_dev, owner, values, status, g, npx);
+            if (npx * 2 >= ntex) {
+                long long nbt = (ntex + 255) / 256;
+                const int gridt = (int)(nbt < (long long)sms * 8 ? nbt : (long long)sms * 8);
+                k_bake_write_texels<CT><<<gridt, 256, 0, st>>>(colors + (long long)f0 * hw * g.Cin, a->writtens_dev, owner, values, g, ntex);
+            } else {
+                k_bake_write<IdT, CT><<<grid, 256, 0, st>>>(ids + (long long)f0 * hw, masks, colors + (long long)f0 * hw * g.Cin,
+                                                            a->writtens_dev, owner, values, status, g, npx);
+            }
         }
     } else {
         float *acc = reinterpret_cast<float *>(ws);
@@ -195,7 +232,8 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
         if (a->phase != 1) {
             long long nb2 = (ntex + 255) / 256;
             const int grid2 = (int)(nb2 < (long long)sms * 8 ? nb2 : (long long)sms * 8);
-            k_bake_finalize<<<grid2, 256, 0, st>>>(acc, wsum, values, a->writtens_dev, ntex, g.C, g.first_mode);
+            k_bake_finalize<<<grid2, 256, 0, st>>>(acc, wsum, values, a->writtens_dev, ntex, g.C, g.first_mode,
+                                                   (g.C == 4 && g.Cin == 3) ? 1 : 0);
         }
     }
     SRX_CUDA_CHECK(cudaGetLastError());

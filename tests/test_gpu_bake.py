@@ -138,3 +138,24 @@ def test_weighted_bake_sharded_phases_equal_single_bake():
         cm.update(colors[sl], ids[sl], normal_depth=nd[sl], phase=2, **kw)
         assert torch.equal(cm._writtens, ref._writtens)
         assert torch.allclose(cm._values.float(), ref._values.float(), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("mode", ["first", "replace"])
+def test_bake_small_update_into_large_atlas(mode):
+    """Few pixels into a large atlas: the pixel-major write kernel (the texel-major one serves views with at least half as
+    many pixels as the atlas has texels); two calls, so `first` must keep what the first call wrote."""
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import CorrespondMap
+    H, tex, k = 64, 128, 3
+    ids = synthetic.make_ids(2, H, H, tex_h=tex, tex_w=tex, k=k, frac_2048=0.0, seed=8)
+    colors = synthetic.make_colors(2, H, H, 3, seed=9)
+    masks = torch.from_numpy(O.idmap_masks(ids.numpy()))
+    values, writtens = O.corrmap_new(k, tex, tex, 4)
+    cm = CorrespondMap(name="t", k=k, height=tex, width=tex, channel_count=4)
+    for f in range(2):
+        O.corrmap_update(values, writtens, colors[f:f + 1].numpy(), ids[f:f + 1].numpy(), mode=mode, masks=masks[f:f + 1].numpy(),
+                         inverse_masks=True, ignore_obj_mat_id=True)
+        cm.update(colors[f:f + 1], ids[f:f + 1], mode=mode, masks=masks[f:f + 1], inverse_masks=True, ignore_obj_mat_id=True)
+    v, w = _atlas(cm)
+    assert np.array_equal(w, writtens)
+    assert np.array_equal(v, values.view(np.uint16))
