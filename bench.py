@@ -579,9 +579,11 @@ def run_bake(args, rank: int, local: int, world: int) -> dict:
                 "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host),
                 "d2h_bytes_per_step": flags_out.numel(), "api": "CorrespondMap.update(color_frames, id_maps, ...)"},
         "gpu_launches": 2 * K,
-        "roofline": {"bound": "hbm", "kernel": "k_bake_accum + k_bake_finalize" if weighted else "k_bake_claim + k_bake_write",
+        "roofline": {"bound": "hbm",
+                     "kernel": "k_bake_accum_pair + k_bake_finalize (one step)" if weighted else "k_bake_claim_pair + k_bake_write_texels (one step)",
                      "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_launch": alg},
+                     "traffic": ncu_traffic("bake_weighted" if weighted else "bake_none") if world == 1 else None,
+                     "peak_source": peak_src, "bytes_per_launch": alg},
     }
 
 

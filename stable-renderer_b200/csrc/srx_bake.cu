@@ -15,6 +15,8 @@
 // weighted sum per texel and a per-texel finalize.
 #include "srx_common.cuh"
 
+#include <type_traits>
+
 enum { BK_ST_INDEX = 0 };
 
 struct BakeGeom {
@@ -26,15 +28,13 @@ struct BakeGeom {
     int frames_total;  // frames in this chunk
 };
 
-template <typename IdT>
-__device__ __forceinline__ bool bake_texel(const IdT *__restrict__ ids, const float *__restrict__ masks, long long i,
-                                           const BakeGeom &g, bool require_id, long long *tex, int *status) {
-    if (masks) {
-        float m = masks[i];
+// mask and id tests of one pixel that is already in registers: true + its texel when the pixel takes part in the bake
+__device__ __forceinline__ bool bake_texel_eval(const IdPx &p, float m, bool has_mask, const BakeGeom &g, bool require_id,
+                                                long long *tex, int *status) {
+    if (has_mask) {
         if (g.inverse_masks) m = __fsub_rn(1.f, m);  // corrmap.py:651-654
         if (!(m > 0.f)) return false;                // corrmap.py:707
     }
-    const IdPx p = load_id(ids + i);
     if (require_id && !id_valid(p)) return false;
     if (!g.ignore_filter) {                         // corrmap.py:710-715
         if (g.sprite >= 0 && p.s != g.sprite) return false;
@@ -52,21 +52,102 @@ __device__ __forceinline__ bool bake_texel(const IdT *__restrict__ ids, const fl
 }
 
 template <typename IdT>
+__device__ __forceinline__ bool bake_texel(const IdT *__restrict__ ids, const float *__restrict__ masks, long long i,
+                                           const BakeGeom &g, bool require_id, long long *tex, int *status) {
+    float m = 0.f;
+    if (masks) {
+        m = masks[i];
+        if (!((g.inverse_masks ? __fsub_rn(1.f, m) : m) > 0.f)) return false;   // masked out: the id is not even loaded
+    }
+    return bake_texel_eval(load_id(ids + i), m, masks != nullptr, g, require_id, tex, status);
+}
+
+// order key of pixel i of the chunk (32-bit arithmetic: a chunk holds fewer than 2^32 pixels): `replace` ranks pixels in
+// (frame, pixel) order, `first` ranks earlier frames higher
+__device__ __forceinline__ unsigned int bake_order1(unsigned int i, unsigned int hw, const BakeGeom &g) {
+    if (!g.first_mode) return i + 1u;
+    const unsigned int f = i / hw;
+    return ((unsigned int)(g.frames_total - 1) - f) * hw + (i - f * hw) + 1u;
+}
+
+// Texel 0 of map 0 is what every pixel WITHOUT an id addresses when the caller passes no masks (all-zero id -> map_index 0,
+// vertexID 0; the reference writes their colours there too).  With `replace` keys growing along the sweep nearly each of those
+// pixels would have to update the same word (measured: the claim pass took 1.4 ms instead of 0.2 ms on config 4).  Claims on
+// texel 0 are therefore reduced per thread, warp and block, and leave the block as one atomic.
+__device__ __forceinline__ void bake_claim_texel0(unsigned int zmax, const uint8_t *__restrict__ writtens,
+                                                  unsigned int *__restrict__ owner, const BakeGeom &g, unsigned int *smax) {
+    zmax = __reduce_max_sync(0xffffffffu, zmax);
+    if ((threadIdx.x & 31) == 0 && zmax) atomicMax(smax, zmax);
+    __syncthreads();
+    if (threadIdx.x == 0 && *smax && !(g.first_mode && writtens[0]) && __ldcg(owner) < *smax) atomicMax(owner, *smax);
+}
+
+template <typename IdT>
 __global__ void __launch_bounds__(256) k_bake_claim(const IdT *__restrict__ ids, const float *__restrict__ masks,
                                                      const uint8_t *__restrict__ writtens, unsigned int *__restrict__ owner,
                                                      int *__restrict__ status, BakeGeom g, long long npx) {
     const long long hw = (long long)g.H * g.W;
+    __shared__ unsigned int smax;
+    if (threadIdx.x == 0) smax = 0u;
+    __syncthreads();
+    unsigned int zmax = 0u;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
         long long tex;
         if (!bake_texel(ids, masks, i, g, false, &tex, status)) continue;
+        const unsigned int order1 = bake_order1((unsigned int)i, (unsigned int)hw, g);
+        if (tex == 0) { zmax = order1 > zmax ? order1 : zmax; continue; }
         if (g.first_mode && writtens[tex]) continue;
-        const long long f = i / hw, pix = i - f * hw;
-        const unsigned int order1 = (unsigned int)((g.first_mode ? (g.frames_total - 1 - f) : f) * hw + pix + 1);
         // the owner word only grows: skip the atomic when a later pixel already claimed the texel (removes almost all
         // traffic to hot texels such as (0,0), which every background pixel addresses when no mask is given)
         if (__ldcg(owner + tex) >= order1) continue;
         atomicMax(owner + tex, order1);
     }
+    bake_claim_texel0(zmax, writtens, owner, g, &smax);
+}
+
+// Two horizontally adjacent pixels per thread: one 256-bit id load, two owner probes in flight (the kernels of this file are
+// chains of dependent loads — ncu: 39 of 40 issue slots stall on the scoreboard with one pixel per thread).
+template <typename IdT>
+__global__ void __launch_bounds__(256) k_bake_claim_pair(const IdT *__restrict__ ids, const float *__restrict__ masks,
+                                                          const uint8_t *__restrict__ writtens, unsigned int *__restrict__ owner,
+                                                          int *__restrict__ status, BakeGeom g, long long npairs) {
+    const unsigned int hw = (unsigned int)((long long)g.H * g.W);
+    __shared__ unsigned int smax;
+    if (threadIdx.x == 0) smax = 0u;
+    __syncthreads();
+    unsigned int zmax = 0u;
+    for (long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x; pr < npairs; pr += (long long)gridDim.x * blockDim.x) {
+        const long long i0 = pr * 2;
+        IdPx a, b;
+        load_id_pair(ids + i0, a, b);
+        float m0 = 0.f, m1 = 0.f;
+        if (masks) {
+            const float2 mm = *reinterpret_cast<const float2 *>(masks + i0);
+            m0 = mm.x; m1 = mm.y;
+        }
+        long long t0 = 0, t1 = 0;
+        bool ok0 = bake_texel_eval(a, m0, masks != nullptr, g, false, &t0, status);
+        bool ok1 = bake_texel_eval(b, m1, masks != nullptr, g, false, &t1, status);
+        if (ok0 && t0 == 0) { const unsigned int o = bake_order1((unsigned int)i0, hw, g); zmax = o > zmax ? o : zmax; ok0 = false; }
+        if (ok1 && t1 == 0) { const unsigned int o = bake_order1((unsigned int)i0 + 1u, hw, g); zmax = o > zmax ? o : zmax; ok1 = false; }
+        if (!(ok0 || ok1)) continue;
+        unsigned int c0 = 0xffffffffu, c1 = 0xffffffffu;
+        if (ok0) c0 = __ldcg(owner + t0);
+        if (ok1) c1 = __ldcg(owner + t1);
+        if (g.first_mode) {
+            if (ok0 && writtens[t0]) ok0 = false;
+            if (ok1 && writtens[t1]) ok1 = false;
+        }
+        const unsigned int o0 = bake_order1((unsigned int)i0, hw, g), o1 = bake_order1((unsigned int)i0 + 1u, hw, g);
+        if (ok0 && ok1 && t0 == t1) {                       // both pixels show the same texel: one atomic with the larger key
+            const unsigned int o = o0 > o1 ? o0 : o1;
+            if (c0 < o) atomicMax(owner + t0, o);
+            continue;
+        }
+        if (ok0 && c0 < o0) atomicMax(owner + t0, o0);
+        if (ok1 && c1 < o1) atomicMax(owner + t1, o1);
+    }
+    bake_claim_texel0(zmax, writtens, owner, g, &smax);
 }
 
 template <typename CT> __device__ __forceinline__ float color_ld(const CT *p);
@@ -152,6 +233,56 @@ __global__ void __launch_bounds__(256) k_bake_accum(const IdT *__restrict__ ids,
     }
 }
 
+__device__ __forceinline__ float bake_weight_bits(unsigned int nz_depth, int mode) {   // low half n_z, high half depth
+    if (mode == SRX_WEIGHT_UNIFORM) return 1.f;
+    const float nz = __half2float(__ushort_as_half((unsigned short)(nz_depth & 0xffffu)));
+    const float vn = fabsf(__fsub_rn(__fmul_rn(2.f, nz), 1.f));
+    float w = __fdiv_rn(1.f, __fadd_rn(fabsf(__fsub_rn(1.f, vn)), 1.f));
+    if (mode == SRX_WEIGHT_VIEW_NORMAL_DEPTH) w = __fmul_rn(w, __half2float(__ushort_as_half((unsigned short)(nz_depth >> 16))));
+    return w;
+}
+
+// RGB float32 colours, two adjacent pixels per thread: 256-bit id load, 128-bit normal+depth load, three 64-bit colour loads.
+template <typename IdT>
+__global__ void __launch_bounds__(256) k_bake_accum_pair(const IdT *__restrict__ ids, const float *__restrict__ masks,
+                                                          const float *__restrict__ colors, const __half *__restrict__ nd,
+                                                          float *__restrict__ acc, float *__restrict__ wsum,
+                                                          int *__restrict__ status, BakeGeom g, int weight_mode, long long npairs) {
+    const bool w_in_alpha = g.C == 4;      // Cin == 3 here: alpha accumulates w * 1
+    for (long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x; pr < npairs; pr += (long long)gridDim.x * blockDim.x) {
+        const long long i0 = pr * 2;
+        IdPx a, b;
+        load_id_pair(ids + i0, a, b);
+        float m0 = 0.f, m1 = 0.f;
+        if (masks) {
+            const float2 mm = *reinterpret_cast<const float2 *>(masks + i0);
+            m0 = mm.x; m1 = mm.y;
+        }
+        long long t0 = 0, t1 = 0;
+        const bool ok0 = bake_texel_eval(a, m0, masks != nullptr, g, true, &t0, status);
+        const bool ok1 = bake_texel_eval(b, m1, masks != nullptr, g, true, &t1, status);
+        if (!(ok0 || ok1)) continue;
+        float w0 = 1.f, w1 = 1.f;
+        if (nd != nullptr && weight_mode != SRX_WEIGHT_UNIFORM) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(nd + i0 * 4);
+            w0 = bake_weight_bits(q.y, weight_mode);
+            w1 = bake_weight_bits(q.w, weight_mode);
+        }
+        const float2 *c = reinterpret_cast<const float2 *>(colors + i0 * 3);
+        const float2 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);       // r0 g0 | b0 r1 | g1 b1
+        if (ok0) {
+            red_add_f32x4(acc + t0 * 4, __fmul_rn(w0, c0.x), g.C > 1 ? __fmul_rn(w0, c0.y) : 0.f, g.C > 2 ? __fmul_rn(w0, c1.x) : 0.f,
+                          w_in_alpha ? w0 : 0.f);
+            if (!w_in_alpha) red_add_f32(wsum + t0, w0);
+        }
+        if (ok1) {
+            red_add_f32x4(acc + t1 * 4, __fmul_rn(w1, c1.y), g.C > 1 ? __fmul_rn(w1, c2.x) : 0.f, g.C > 2 ? __fmul_rn(w1, c2.y) : 0.f,
+                          w_in_alpha ? w1 : 0.f);
+            if (!w_in_alpha) red_add_f32(wsum + t1, w1);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_bake_finalize(const float *__restrict__ acc, const float *__restrict__ wsum,
                                                         __half *__restrict__ values, uint8_t *__restrict__ writtens,
                                                         long long ntex, int C, int first_mode, int w_in_alpha) {
@@ -206,7 +337,15 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
             const int grid = (int)(nb < (long long)sms * 8 ? nb : (long long)sms * 8);
             const float *masks = a->masks_dev ? a->masks_dev + (long long)f0 * hw : nullptr;
             SRX_CUDA_CHECK(cudaMemsetAsync(owner, 0, (size_t)ntex * 4, st));
-            k_bake_claim<IdT><<<grid, 256, 0, st>>>(ids + (long long)f0 * hw, masks, a->writtens_dev, owner, status, g, npx);
+            const bool pair_ok = (npx & 1) == 0 && (reinterpret_cast<uintptr_t>(ids + (long long)f0 * hw) & 31) == 0 &&
+                                 (reinterpret_cast<uintptr_t>(masks) & 7) == 0;
+            if (pair_ok) {
+                long long nbp = (npx / 2 + 255) / 256;
+                const int gridp = (int)(nbp < (long long)sms * 8 ? nbp : (long long)sms * 8);
+                k_bake_claim_pair<IdT><<<gridp, 256, 0, st>>>(ids + (long long)f0 * hw, masks, a->writtens_dev, owner, status, g, npx / 2);
+            } else {
+                k_bake_claim<IdT><<<grid, 256, 0, st>>>(ids + (long long)f0 * hw, masks, a->writtens_dev, owner, status, g, npx);
+            }
             if (npx * 2 >= ntex) {
                 long long nbt = (ntex + 255) / 256;
                 const int gridt = (int)(nbt < (long long)sms * 8 ? nbt : (long long)sms * 8);
@@ -226,8 +365,19 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
             const long long npx = (long long)a->frames * hw;
             long long nb = (npx + 255) / 256;
             const int grid = (int)(nb < (long long)sms * 8 ? nb : (long long)sms * 8);
-            k_bake_accum<IdT, CT><<<grid, 256, 0, st>>>(ids, a->masks_dev, colors, reinterpret_cast<const __half *>(a->normal_depth_dev),
-                                                        acc, wsum, status, g, a->weight_mode, npx);
+            const bool pair_ok = std::is_same<CT, float>::value && g.Cin == 3 && (npx & 1) == 0 &&
+                                 (reinterpret_cast<uintptr_t>(ids) & 31) == 0 && (reinterpret_cast<uintptr_t>(a->masks_dev) & 7) == 0 &&
+                                 (reinterpret_cast<uintptr_t>(a->colors_dev) & 7) == 0 && (reinterpret_cast<uintptr_t>(a->normal_depth_dev) & 15) == 0;
+            if (pair_ok) {
+                long long nbp = (npx / 2 + 255) / 256;
+                const int gridp = (int)(nbp < (long long)sms * 8 ? nbp : (long long)sms * 8);
+                k_bake_accum_pair<IdT><<<gridp, 256, 0, st>>>(ids, a->masks_dev, reinterpret_cast<const float *>(a->colors_dev),
+                                                              reinterpret_cast<const __half *>(a->normal_depth_dev), acc, wsum, status, g,
+                                                              a->weight_mode, npx / 2);
+            } else {
+                k_bake_accum<IdT, CT><<<grid, 256, 0, st>>>(ids, a->masks_dev, colors, reinterpret_cast<const __half *>(a->normal_depth_dev),
+                                                            acc, wsum, status, g, a->weight_mode, npx);
+            }
         }
         if (a->phase != 1) {
             long long nb2 = (ntex + 255) / 256;

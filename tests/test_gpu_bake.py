@@ -159,3 +159,58 @@ def test_bake_small_update_into_large_atlas(mode):
     v, w = _atlas(cm)
     assert np.array_equal(w, writtens)
     assert np.array_equal(v, values.view(np.uint16))
+
+
+@pytest.mark.parametrize("shape", [(3, 9, 7), (2, 16, 24)])
+def test_bake_odd_and_even_pixel_counts_all_paths(shape):
+    """Odd pixel counts take the one-pixel-per-thread kernels, even ones the pair kernels; reference modes bit exact, weighted
+    bake within one fp16 ulp, with RGB colours (weight sums in the alpha channel), RGBA colours and fp16 colours (scalar)."""
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import CorrespondMap
+    F, H, W = shape
+    tex, k = 16, 2
+    ids = synthetic.make_ids(F, H, W, tex_h=tex, tex_w=tex, k=k, frac_2048=0.05, seed=21)
+    masks = torch.from_numpy(O.idmap_masks(ids.numpy()))
+    nd = synthetic.make_normal_depth(F, H, W, seed=6)
+    for cin, cdt in ((3, torch.float32), (4, torch.float32), (3, torch.float16)):
+        colors = synthetic.make_colors(F, H, W, cin, seed=5).to(cdt)
+        for mode in ("replace", "first"):
+            values, writtens = O.corrmap_new(k, tex, tex, 4)
+            O.corrmap_update(values, writtens, colors.float().numpy(), ids.numpy(), mode=mode, masks=masks.numpy(),
+                             inverse_masks=True, ignore_obj_mat_id=True)
+            cm = CorrespondMap(name="t", k=k, height=tex, width=tex, channel_count=4)
+            cm.update(colors, ids, mode=mode, masks=masks, inverse_masks=True, ignore_obj_mat_id=True)
+            v, w = _atlas(cm)
+            assert np.array_equal(w, writtens), (cin, cdt, mode)
+            assert np.array_equal(v, values.view(np.uint16)), (cin, cdt, mode)
+        acc = np.zeros((k * k, tex * tex, 4)); wsum = np.zeros((k * k, tex * tex))
+        O.corrmap_update_weighted(acc, wsum, colors.float().numpy(), ids.numpy(), nd.float().numpy(), "view_normal_depth")
+        values, writtens = O.corrmap_new(k, tex, tex, 4)
+        O.corrmap_finalize_weighted(values, writtens, acc, wsum)
+        cm = CorrespondMap(name="t", k=k, height=tex, width=tex, channel_count=4)
+        cm.update(colors, ids, mode="replace", weight_mode="view_normal_depth", normal_depth=nd)
+        assert np.array_equal(cm._writtens.cpu().numpy(), writtens), (cin, cdt)
+        assert_close(t2n(cm._values), values.astype(np.float32), 1e-3, 1e-6, f"weighted {cin} {cdt}")
+
+
+@pytest.mark.parametrize("shape", [(3, 9, 7), (4, 64, 64)])
+@pytest.mark.parametrize("mode", ["replace", "first"])
+def test_bake_without_masks_background_goes_to_texel_zero(shape, mode):
+    """No masks, no sprite filter: pixels without an id carry (0,0,0,0) and all write texel 0 of map 0, like in the reference
+    (corrmap.py:735 with nothing filtered).  Those claims are aggregated per block in the kernel; the winner must still be the
+    reference's (last pixel of the last / earliest frame)."""
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import CorrespondMap
+    F, H, W = shape
+    tex, k = 16, 2
+    ids = synthetic.make_ids(F, H, W, tex_h=tex, tex_w=tex, k=k, frac_2048=0.0, seed=33)
+    assert (ids == 0).all(dim=-1).any()
+    colors = synthetic.make_colors(F, H, W, 3, seed=12)
+    values, writtens = O.corrmap_new(k, tex, tex, 4)
+    cm = CorrespondMap(name="t", k=k, height=tex, width=tex, channel_count=4)
+    for sl in (slice(0, F - 1), slice(F - 1, F)):                      # two calls: `first` keeps texel 0 from the first call
+        O.corrmap_update(values, writtens, colors[sl].numpy(), ids[sl].numpy(), mode=mode, ignore_obj_mat_id=True)
+        cm.update(colors[sl], ids[sl], mode=mode, ignore_obj_mat_id=True)
+    v, w = _atlas(cm)
+    assert w[0, 0] and np.array_equal(w, writtens)
+    assert np.array_equal(v, values.view(np.uint16))
