@@ -72,14 +72,13 @@ __device__ __forceinline__ unsigned int bake_order1(unsigned int i, unsigned int
 
 // Texel 0 of map 0 is what every pixel WITHOUT an id addresses when the caller passes no masks (all-zero id -> map_index 0,
 // vertexID 0; the reference writes their colours there too).  With `replace` keys growing along the sweep nearly each of those
-// pixels would have to update the same word (measured: the claim pass took 1.4 ms instead of 0.2 ms on config 4).  Claims on
-// texel 0 are therefore reduced per thread, warp and block, and leave the block as one atomic.
+// pixels would have to update the same word (measured: the claim pass took 1.4 ms instead of 0.3 ms on config 4).  Claims on
+// texel 0 are therefore reduced per thread and warp and leave the warp as one atomic when its loop ends (a block-level
+// reduction cost 17 % of the warps' time at the barrier: warps over background finish early).
 __device__ __forceinline__ void bake_claim_texel0(unsigned int zmax, const uint8_t *__restrict__ writtens,
-                                                  unsigned int *__restrict__ owner, const BakeGeom &g, unsigned int *smax) {
+                                                  unsigned int *__restrict__ owner, const BakeGeom &g) {
     zmax = __reduce_max_sync(0xffffffffu, zmax);
-    if ((threadIdx.x & 31) == 0 && zmax) atomicMax(smax, zmax);
-    __syncthreads();
-    if (threadIdx.x == 0 && *smax && !(g.first_mode && writtens[0]) && __ldcg(owner) < *smax) atomicMax(owner, *smax);
+    if ((threadIdx.x & 31) == 0 && zmax && !(g.first_mode && writtens[0]) && __ldcg(owner) < zmax) atomicMax(owner, zmax);
 }
 
 template <typename IdT>
@@ -87,9 +86,6 @@ __global__ void __launch_bounds__(256) k_bake_claim(const IdT *__restrict__ ids,
                                                      const uint8_t *__restrict__ writtens, unsigned int *__restrict__ owner,
                                                      int *__restrict__ status, BakeGeom g, long long npx) {
     const long long hw = (long long)g.H * g.W;
-    __shared__ unsigned int smax;
-    if (threadIdx.x == 0) smax = 0u;
-    __syncthreads();
     unsigned int zmax = 0u;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
         long long tex;
@@ -102,34 +98,42 @@ __global__ void __launch_bounds__(256) k_bake_claim(const IdT *__restrict__ ids,
         if (__ldcg(owner + tex) >= order1) continue;
         atomicMax(owner + tex, order1);
     }
-    bake_claim_texel0(zmax, writtens, owner, g, &smax);
+    bake_claim_texel0(zmax, writtens, owner, g);
 }
 
 // NP pairs of horizontally adjacent pixels per thread (2 NP consecutive pixels): one 256-bit id load per pair, all owner
 // probes in flight together.  The pass is a chain of dependent loads (ids -> owner word -> atomic); ncu: scoreboard stalls on
 // top, DRAM at 44 %, 45 G atomic sectors/s.
 template <typename IdT, int NP>
+__device__ __forceinline__ void bake_load_group(const IdT *__restrict__ ids, const float *__restrict__ masks, long long i0,
+                                                IdPx (&px)[2 * NP], float (&m)[2 * NP]) {
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        load_id_pair(ids + i0 + 2 * q, px[2 * q], px[2 * q + 1]);
+        m[2 * q] = 0.f; m[2 * q + 1] = 0.f;
+        if (masks) {
+            const float2 mm = *reinterpret_cast<const float2 *>(masks + i0 + 2 * q);
+            m[2 * q] = mm.x; m[2 * q + 1] = mm.y;
+        }
+    }
+}
+
+template <typename IdT, int NP>
 __global__ void __launch_bounds__(256) k_bake_claim_pair(const IdT *__restrict__ ids, const float *__restrict__ masks,
                                                           const uint8_t *__restrict__ writtens, unsigned int *__restrict__ owner,
                                                           int *__restrict__ status, BakeGeom g, long long ngroups) {
     const unsigned int hw = (unsigned int)((long long)g.H * g.W);
-    __shared__ unsigned int smax;
-    if (threadIdx.x == 0) smax = 0u;
-    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
     unsigned int zmax = 0u;
-    for (long long gr = (long long)blockIdx.x * blockDim.x + threadIdx.x; gr < ngroups; gr += (long long)gridDim.x * blockDim.x) {
+    long long gr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    IdPx px[2 * NP], nx[2 * NP];
+    float m[2 * NP], nm[2 * NP];
+    if (gr < ngroups) bake_load_group<IdT, NP>(ids, masks, gr * (2 * NP), px, m);
+    while (gr < ngroups) {
+        // the ids of the next round are requested before this round's owner probes: the two HBM / L2 round trips of a round
+        // overlap (ncu source view: 36 % of the stall samples sat on the first use of the ids, 30 % on the owner word)
+        if (gr + stride < ngroups) bake_load_group<IdT, NP>(ids, masks, (gr + stride) * (2 * NP), nx, nm);
         const long long i0 = gr * (2 * NP);
-        IdPx px[2 * NP];
-        float m[2 * NP];
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-            load_id_pair(ids + i0 + 2 * q, px[2 * q], px[2 * q + 1]);
-            m[2 * q] = 0.f; m[2 * q + 1] = 0.f;
-            if (masks) {
-                const float2 mm = *reinterpret_cast<const float2 *>(masks + i0 + 2 * q);
-                m[2 * q] = mm.x; m[2 * q + 1] = mm.y;
-            }
-        }
         long long t[2 * NP];
         unsigned int cur[2 * NP], ord[2 * NP];
         bool ok[2 * NP];
@@ -150,8 +154,11 @@ __global__ void __launch_bounds__(256) k_bake_claim_pair(const IdT *__restrict__
             if (k + 1 < 2 * NP && ok[k + 1] && t[k + 1] == t[k] && ord[k + 1] > ord[k]) continue;
             if (cur[k] < ord[k]) atomicMax(owner + t[k], ord[k]);
         }
+#pragma unroll
+        for (int k = 0; k < 2 * NP; ++k) { px[k] = nx[k]; m[k] = nm[k]; }
+        gr += stride;
     }
-    bake_claim_texel0(zmax, writtens, owner, g, &smax);
+    bake_claim_texel0(zmax, writtens, owner, g);
 }
 
 template <typename CT> __device__ __forceinline__ float color_ld(const CT *p);
@@ -253,18 +260,15 @@ __global__ void __launch_bounds__(256) k_bake_accum_pair(const IdT *__restrict__
                                                           float *__restrict__ acc, float *__restrict__ wsum,
                                                           int *__restrict__ status, BakeGeom g, int weight_mode, long long npairs) {
     const bool w_in_alpha = g.C == 4;      // Cin == 3 here: alpha accumulates w * 1
+    // (requesting the next round's ids before this round's colours, as the claim kernel does, measured 9 % slower here)
     for (long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x; pr < npairs; pr += (long long)gridDim.x * blockDim.x) {
         const long long i0 = pr * 2;
-        IdPx a, b;
-        load_id_pair(ids + i0, a, b);
-        float m0 = 0.f, m1 = 0.f;
-        if (masks) {
-            const float2 mm = *reinterpret_cast<const float2 *>(masks + i0);
-            m0 = mm.x; m1 = mm.y;
-        }
+        IdPx px[2];
+        float m[2];
+        bake_load_group<IdT, 1>(ids, masks, i0, px, m);
         long long t0 = 0, t1 = 0;
-        const bool ok0 = bake_texel_eval(a, m0, masks != nullptr, g, true, &t0, status);
-        const bool ok1 = bake_texel_eval(b, m1, masks != nullptr, g, true, &t1, status);
+        const bool ok0 = bake_texel_eval(px[0], m[0], masks != nullptr, g, true, &t0, status);
+        const bool ok1 = bake_texel_eval(px[1], m[1], masks != nullptr, g, true, &t1, status);
         if (!(ok0 || ok1)) continue;
         float w0 = 1.f, w1 = 1.f;
         if (nd != nullptr && weight_mode != SRX_WEIGHT_UNIFORM) {
