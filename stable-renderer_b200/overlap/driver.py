@@ -123,4 +123,4 @@ class ResizeOverlap(Overlap):
         stack = torch.stack(frame_seq, dim=0).contiguous()      # [T,B,C,h,w]
         T, B, Cc, h, w = stack.shape
         self._run(stack.view(T, B * Cc, h, w), corr_map, alpha, kwargs.get("view_normal_map"))
-        return [stack[i] for i in range(T)]
+        return list(stack.unbind(0))
