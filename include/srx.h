@@ -237,6 +237,14 @@ int64_t srx_legacy_workspace_bytes(const srx_legacy_desc *desc);
 /* Errors (after a sync) with SRX_ERR_KEY_RANGE when an id component does not fit the packed 64-bit key. */
 int srx_legacy_overlap(const srx_legacy_desc *desc, const srx_legacy_args *args, void *stream);
 
+/* kernel_radius > 0 (overlap.py:61-80,137-145): the reference pools the diagonal neighbours (y+d, x+d), d in [-r, r], and
+ * writes every blended trace into the storage it keeps reading, trace after trace in dict order — a Gauss-Seidel sweep whose
+ * result depends on that order.  This entry reproduces it: traces ranked in insertion order, entries in (frame,row,col) order,
+ * one CTA walks the traces strictly in sequence (entries of a trace in parallel).  Same descriptor / arguments as
+ * srx_legacy_overlap (radius 0 gives the same result as srx_legacy_overlap, more slowly); its own, larger workspace. */
+int64_t srx_legacy_ordered_workspace_bytes(const srx_legacy_desc *desc);
+int srx_legacy_overlap_ordered(const srx_legacy_desc *desc, const srx_legacy_args *args, int kernel_radius, void *stream);
+
 /* CorrespondenceMap maintenance (legacy data_classes/correspondence_map.py).  The map IS the id buffers: a key is the id
  * tuple (after merge_nearby's floor division), deleting a key clears the ids of every pixel that carries it.
  *   srx_corrmap_first_appearance: mask[i] = 1 where pixel i introduces its key — the marked pixels, in index order, are the

@@ -99,6 +99,8 @@ _PROTOTYPES = {
     "srx_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(srx_plan_info)]),
     "srx_plan_bind_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "srx_plan_bind_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "srx_legacy_ordered_workspace_bytes": (C.c_int64, [C.POINTER(srx_legacy_desc)]),
+    "srx_legacy_overlap_ordered": (C.c_int, [C.POINTER(srx_legacy_desc), C.POINTER(srx_legacy_args), C.c_int, C.c_void_p]),
     "srx_corrmap_keys_workspace_bytes": (C.c_int64, [C.c_int64]),
     "srx_corrmap_first_appearance": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_int64, C.c_void_p]),

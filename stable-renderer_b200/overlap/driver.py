@@ -1,8 +1,9 @@
 """`Overlap` and `ResizeOverlap` (reference: legacy_codes/stable_rendering_algo/overlap/overlap.py:18-222).
 
 Same constructor and call signatures; one `srx_legacy_overlap` call replaces the per-vertex Python loop.
-kernel_radius > 0 is rejected: in the reference it is an in-place (Gauss–Seidel, dict-order dependent) update
-(overlap.py:97,136-145) that has no parallel definition — see DESIGN.md §6."""
+With kernel_radius > 0 the reference is an in-place (Gauss–Seidel) update in dict order (overlap.py:97,136-145):
+`srx_legacy_overlap_ordered` walks the traces in that order on the GPU (entries of a trace in parallel, traces in
+sequence) — see DESIGN.md §3."""
 from __future__ import annotations
 
 import ctypes as C
@@ -34,7 +35,7 @@ class Overlap:
         self._verbose = value
 
     # ------------------------------------------------------------------------------------------------------------------
-    def _run(self, stack: torch.Tensor, corr_map: CorrespondenceMap, alpha: float, view_normal_map) -> None:
+    def _run(self, stack: torch.Tensor, corr_map: CorrespondenceMap, alpha: float, view_normal_map, radius: int = 0) -> None:
         """stack [T, B*C, h, w] contiguous CUDA tensor, updated in place."""
         if not stack.is_cuda:
             raise _lib.SrxUnavailable("latents must be CUDA tensors (there is no CPU path)")
@@ -53,7 +54,7 @@ class Overlap:
         d.channels, d.lat_h, d.lat_w = CC, h, w
         d.merge_len = corr_map.merge_len
         d.strategy = _lib.SRX_STRATEGY[strategy]
-        need = int(lib.srx_legacy_workspace_bytes(C.byref(d)))
+        need = int((lib.srx_legacy_ordered_workspace_bytes if radius > 0 else lib.srx_legacy_workspace_bytes)(C.byref(d)))
         if need < 0:
             _lib.check(_lib.SRX_ERR_INVALID)
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != stack.device:
@@ -71,16 +72,17 @@ class Overlap:
             a.view_normal_dev = vn.data_ptr()
         a.workspace_dev, a.workspace_bytes = self._workspace.data_ptr(), self._workspace.numel()
         with torch.cuda.device(stack.device):
-            _lib.check(lib.srx_legacy_overlap(C.byref(d), C.byref(a), _lib.current_stream_ptr(stack.device)))
+            stream = _lib.current_stream_ptr(stack.device)
+            if radius > 0:
+                _lib.check(lib.srx_legacy_overlap_ordered(C.byref(d), C.byref(a), int(radius), stream))
+            else:
+                _lib.check(lib.srx_legacy_overlap(C.byref(d), C.byref(a), stream))
 
     def _schedule(self, step, timestep):
+        """(alpha, kernel_radius) for this call (overlap.py:100-101: the radius is `int()`-truncated)."""
         alpha = self.alpha_scheduler(step, timestep)
         radius = int(self.kernel_radius_scheduler(step, timestep))
-        if radius > 0:
-            raise NotImplementedError(
-                "kernel_radius > 0 is an order-dependent in-place update in the reference (overlap.py:97,136-145) "
-                "and is not supported; schedule the radius to 0")
-        return float(alpha)
+        return float(alpha), max(radius, 0)
 
     @torch.no_grad()
     def __call__(self, frame_seq: List[torch.Tensor], corr_map: CorrespondenceMap, step: int = None,
@@ -88,10 +90,10 @@ class Overlap:
         """frame_seq: T tensors [B,C,H,W] at the correspondence map's resolution -> stack [T,B,C,H,W] (overlap.py:83-152)."""
         assert frame_seq[0].shape[2:] == (corr_map.height, corr_map.width), \
             f"frame shape {frame_seq[0].shape[2:]} does not match corr_map shape {(corr_map.height, corr_map.width)}"
-        alpha = self._schedule(step, timestep)
+        alpha, radius = self._schedule(step, timestep)
         stack = torch.stack(frame_seq, dim=0).contiguous()      # [T,B,C,H,W], a fresh tensor like the reference's
         T, B, Cc, H, W = stack.shape
-        self._run(stack.view(T, B * Cc, H, W), corr_map, alpha, kwargs.get("view_normal_map"))
+        self._run(stack.view(T, B * Cc, H, W), corr_map, alpha, kwargs.get("view_normal_map"), radius)
         return stack
 
 
@@ -119,8 +121,8 @@ class ResizeOverlap(Overlap):
             return frame_seq                                    # overlap.py:200-201
         if self._interpolate_mode != "nearest":
             raise NotImplementedError("only interpolate_mode='nearest' (the reference default) is supported")
-        alpha = self._schedule(step, timestep)
+        alpha, radius = self._schedule(step, timestep)
         stack = torch.stack(frame_seq, dim=0).contiguous()      # [T,B,C,h,w]
         T, B, Cc, h, w = stack.shape
-        self._run(stack.view(T, B * Cc, h, w), corr_map, alpha, kwargs.get("view_normal_map"))
+        self._run(stack.view(T, B * Cc, h, w), corr_map, alpha, kwargs.get("view_normal_map"), radius)
         return list(stack.unbind(0))

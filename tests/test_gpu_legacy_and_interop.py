@@ -34,7 +34,7 @@ def test_resize_overlap_vs_reference_golden(golden, strategy, cm_name):
     assert_close(t2n(got), g[f"out_{strategy}_r0_{cm_name}"], 1e-5, 3e-6, f"{strategy}/{cm_name}")
 
 
-def test_resize_overlap_alpha_zero_and_radius():
+def test_resize_overlap_alpha_zero_and_unknown_algorithm():
     from stable_renderer_b200.overlap import CorrespondenceMap, ResizeOverlap, overlap_algorithm_factory
     ids = torch.ones(2, 16, 16, 4, dtype=torch.int32).cuda()
     cmap = CorrespondenceMap.from_ids(ids)
@@ -42,11 +42,62 @@ def test_resize_overlap_alpha_zero_and_radius():
     a_s, r_s = _schedulers(0.0)
     out = ResizeOverlap(a_s, r_s, overlap_algorithm_factory("average"), verbose=False)(frames, cmap, step=0, timestep=500)
     assert out is frames                                     # alpha == 0 returns the input list (overlap.py:200-201)
-    a_s, r_s = _schedulers(0.5, 1.0)
-    with pytest.raises(NotImplementedError):
-        ResizeOverlap(a_s, r_s, overlap_algorithm_factory("average"), verbose=False)(frames, cmap, step=0, timestep=500)
     with pytest.raises(ValueError):
         overlap_algorithm_factory("bogus")
+
+
+@pytest.mark.parametrize("strategy", O.STRATEGIES)
+@pytest.mark.parametrize("cm_name", ["full", "merge4"])
+def test_resize_overlap_radius1_vs_reference_golden(golden, strategy, cm_name):
+    """kernel_radius = 1: the reference's in-place sweep in dict order (overlap.py:97,136-145), reproduced trace after trace."""
+    from stable_renderer_b200.overlap import CorrespondenceMap, ResizeOverlap, overlap_algorithm_factory
+    g = golden("legacy_resize_overlap")
+    cmap = CorrespondenceMap.from_ids(torch.from_numpy(g["ids"]).cuda())
+    if cm_name == "merge4":
+        cmap.merge_nearby(4)
+    a_s, r_s = _schedulers(float(g["alpha"]), 1.0)
+    ov = ResizeOverlap(a_s, r_s, overlap_algorithm_factory(strategy), verbose=False)
+    frames = [torch.from_numpy(f).float().cuda() for f in g["frames"]]
+    outs = ov(frames, cmap, step=0, timestep=500, view_normal_map=torch.from_numpy(g["view_normal"]).float().cuda())
+    assert_close(t2n(torch.stack(outs)), g[f"out_{strategy}_r1_{cm_name}"], 2e-5, 5e-6, f"{strategy}/{cm_name} radius 1")
+
+
+@pytest.mark.parametrize("strategy", ["average", "pixel_distance"])
+@pytest.mark.parametrize("radius", [0, 2])
+def test_overlap_full_resolution_with_radius_vs_oracle(strategy, radius):
+    """Overlap.__call__ at map resolution through the ordered sweep: radius 2, and radius 0 (must equal the unordered kernels)."""
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.overlap import CorrespondenceMap, Overlap, overlap_algorithm_factory
+    T, H = 4, 40
+    ids = synthetic.make_ids(T, H, H, tex_h=20, tex_w=20, n_obj=2, seed=19)
+    gen = torch.Generator().manual_seed(2)
+    frames = [torch.randn(2, 4, H, H, generator=gen) for _ in range(T)]
+    want = O.legacy_overlap(torch.stack(frames).numpy(), ids.numpy(), 0.6, strategy, kernel_radius=radius)
+    a_s, r_s = _schedulers(0.6, float(radius))
+    ov = Overlap(a_s, r_s, overlap_algorithm_factory(strategy), verbose=False)
+    cmap = CorrespondenceMap.from_ids(ids.cuda())
+    if radius == 0:                                   # force the ordered entry for radius 0 as well
+        stack = torch.stack([f.cuda() for f in frames]).contiguous()
+        ov._run(stack.view(T, 8, H, H), cmap, 0.6, None, radius=0)
+        got0 = stack.clone()
+        from stable_renderer_b200 import _lib
+        import ctypes as C
+        lib = _lib.load()
+        d = _lib.srx_legacy_desc()
+        d.id_dtype, d.frames, d.height, d.width = _lib.torch_dtype_code(torch.int32), T, H, H
+        d.channels, d.lat_h, d.lat_w, d.merge_len, d.strategy = 8, H, H, 0, _lib.SRX_STRATEGY[strategy]
+        ws = torch.empty(int(lib.srx_legacy_ordered_workspace_bytes(C.byref(d))), dtype=torch.uint8, device="cuda")
+        stack2 = torch.stack([f.cuda() for f in frames]).contiguous()
+        a = _lib.srx_legacy_args()
+        a.x_dev, a.x_dtype, a.ids_dev, a.alpha = stack2.data_ptr(), _lib.SRX_F32, cmap.device_ids(stack2.device).data_ptr(), 0.6
+        a.workspace_dev, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(lib.srx_legacy_overlap_ordered(C.byref(d), C.byref(a), 0, _lib.current_stream_ptr(stack2.device)))
+        torch.cuda.synchronize()
+        assert_close(t2n(stack2), t2n(got0), 1e-5, 3e-6, "ordered radius 0 vs unordered kernels")
+        got = stack2
+    else:
+        got = ov([f.cuda() for f in frames], cmap, step=0, timestep=500)
+    assert_close(t2n(got), want, 2e-5, 5e-6, f"{strategy} radius {radius}")
 
 
 @pytest.mark.parametrize("strategy", O.STRATEGIES)
