@@ -528,8 +528,6 @@ def run_bake(args, rank: int, local: int, world: int) -> dict:
     nd = synthetic.make_normal_depth(V, H, H, device=dev, frame_offset=rank * V)
     cm = CorrespondMap(name="bench", k=1, height=tex, width=tex, channel_count=4, device=dev)
     K, Wm = args.steps, args.warmup
-    if world > 1 and args.bake_weight == "none":
-        raise SystemExit("the reference bake modes are order dependent (last pixel wins): only the weighted bake shards over GPUs")
     import torch.distributed as dist
     mode = dict(mode="replace", weight_mode=args.bake_weight, normal_depth=nd if args.bake_weight.startswith("view") else None,
                 process_group=dist.group.WORLD if world > 1 else None)

@@ -299,9 +299,18 @@ typedef struct srx_bake_args {
     int phase;                 /* weighted bake only: 0 = accumulate + finalize (default); 1 = clear + accumulate the weighted
                                   sums of these views into the workspace; 2 = finalize the atlas from the workspace.  View-sharded
                                   multi-GPU bakes run phase 1 per rank, sum the first srx_bake_workspace_bytes() - 256 bytes of
-                                  the workspaces as float32 (all-reduce), then phase 2 on every rank. */
+                                  the workspaces as float32 (all-reduce), then phase 2 on every rank.
+                                  Reference modes (weight NONE), view-sharded: 1 = claim with order keys that number the views of
+                                  all ranks (frame_offset / frames_global below) -> MAX all-reduce of the first k2*texels int32
+                                  words of the workspace; 2 = write the texels this rank's views won into the workspace's partial
+                                  atlas -> SUM all-reduce of that region as int32 words (each texel is non-zero on one rank only);
+                                  3 = copy the claimed texels into the atlas.  Workspace: srx_bake_sharded_workspace_bytes(). */
+    int frame_offset;          /* view-sharded reference modes: index of this rank's first view among all ranks' views */
+    int frames_global;         /* ... and the number of views of all ranks together (frames_global * H * W < 2^31) */
 } srx_bake_args;
 int64_t srx_bake_workspace_bytes(int k2, int texels, int channels, int weight_mode);
+/* [owner words k2*texels*4, 256-aligned][256 status][partial atlas k2*texels*channels*2, 256-aligned] */
+int64_t srx_bake_sharded_workspace_bytes(int k2, int texels, int channels);
 /* Errors with SRX_ERR_INDEX (after a sync) when a kept pixel addresses a texel outside the atlas. */
 int srx_bake_update(const srx_bake_args *args, void *stream);
 

@@ -70,7 +70,8 @@ class srx_bake_args(C.Structure):
                 ("ids_dev", C.c_void_p), ("id_dtype", C.c_int), ("masks_dev", C.c_void_p), ("inverse_masks", C.c_int),
                 ("frames", C.c_int), ("height", C.c_int), ("width", C.c_int), ("sprite_id", C.c_int),
                 ("material_id", C.c_int), ("ignore_obj_mat_id", C.c_int), ("mode", C.c_int), ("weight_mode", C.c_int),
-                ("normal_depth_dev", C.c_void_p), ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_int64), ("phase", C.c_int)]
+                ("normal_depth_dev", C.c_void_p), ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_int64), ("phase", C.c_int),
+                ("frame_offset", C.c_int), ("frames_global", C.c_int)]
 
 
 class srx_gbuffer(C.Structure):
@@ -111,6 +112,7 @@ _PROTOTYPES = {
                                           C.c_void_p, C.c_int64, C.c_void_p]),
     "srx_corrmap_noise_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srx_bake_sharded_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "srx_atlas_quantize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "srx_atlas_dequantize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "srx_group_rank_workspace_ints": (C.c_int64, [C.c_int64]),

@@ -252,14 +252,16 @@ class CorrespondMap:
     def update(self, color_frames, id_maps, spriteID: int | None = None, materialID: int | None = None,
                mode: UpdateMode = "first_avg", masks=None, inverse_masks: bool = False, ignore_obj_mat_id: bool = False,
                weight_mode: BakeWeight = "none", normal_depth: Optional[Tensor] = None, process_group=None,
-               phase: int = 0):
+               phase: int = 0, frame_offset: int = 0, frames_global: int = 0):
         """`CorrespondMap.update` (reference corrmap.py:578-670): same arguments; all frames go to the GPU in one call.
 
         weight_mode / normal_depth select the depth/normal-weighted multi-view bake, which the
         reference lists as TODO (README.md:18-19); "none" is the reference behaviour.
-        process_group: view-sharded multi-GPU bake (weighted modes only): every rank accumulates its own views, the
-        weighted sums are all-reduced, every rank finalises the same atlas.  `phase` (1 accumulate / 2 finalise) exposes
-        the two halves for callers that do the exchange themselves."""
+        process_group: view-sharded multi-GPU bake; every rank passes its own contiguous block of views (rank order = view
+        order) and ends with the same atlas.  Weighted modes: the weighted sums are all-reduced (`phase` 1 accumulate /
+        2 finalise for callers that do the exchange themselves).  Reference modes: the order keys number the views of all
+        ranks, the claims are MAX-reduced, the ranks' winning texels SUM-reduced (`phase` 1 claim / 2 write / 3 merge with
+        `frame_offset`, `frames_global` for callers that do the exchange themselves)."""
         if mode not in ("replace", "replace_avg", "first", "first_avg"):
             raise ValueError(f"unknown update mode {mode}")
         colors = self._stack(color_frames, "color_frames")
@@ -304,7 +306,13 @@ class CorrespondMap:
                 raise ValueError("normal_depth must be [F,H,W,4]")
         lib = _lib.load()
         wm = _lib.SRX_BAKE_WEIGHT[weight_mode]
+        sharded = process_group is not None
+        if sharded:
+            import torch.distributed as dist
+            sharded = dist.get_world_size(process_group) > 1
         need = int(lib.srx_bake_workspace_bytes(self.k * self.k, self.height * self.width, self.channel_count, wm))
+        if wm == 0 and (sharded or phase):
+            need = int(lib.srx_bake_sharded_workspace_bytes(self.k * self.k, self.height * self.width, self.channel_count))
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         a = _lib.srx_bake_args()
@@ -323,16 +331,27 @@ class CorrespondMap:
         a.weight_mode = wm
         a.normal_depth_dev = nd.data_ptr() if nd is not None else None
         a.workspace_dev, a.workspace_bytes = self._workspace.data_ptr(), self._workspace.numel()
-        sharded = process_group is not None
-        if sharded:
-            import torch.distributed as dist
-            sharded = dist.get_world_size(process_group) > 1
-        if sharded and wm == 0:
-            raise _lib.SrxError("view-sharded bakes need a weight_mode: the reference modes keep the LAST pixel in frame order, "
-                                "which is not a sum (SURVEY.md §8e)")
+        a.frame_offset, a.frames_global = int(frame_offset), int(frames_global)
         with torch.cuda.device(self.device):
             stream = _lib.current_stream_ptr(self.device)
-            if sharded:
+            if sharded and wm == 0:
+                # reference modes: "last pixel in view order wins" is a maximum over order keys, not a sum
+                ntex = self.k * self.k * self.height * self.width
+                counts = torch.zeros(dist.get_world_size(process_group), dtype=torch.int64, device=self.device)
+                counts[dist.get_rank(process_group)] = ids.shape[0]
+                dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=process_group)
+                counts = counts.tolist()
+                a.frame_offset, a.frames_global = int(sum(counts[:dist.get_rank(process_group)])), int(sum(counts))
+                a.phase = 1
+                _lib.check(lib.srx_bake_update(C.byref(a), stream))
+                dist.all_reduce(self._workspace[:ntex * 4].view(torch.int32), op=dist.ReduceOp.MAX, group=process_group)
+                a.phase = 2
+                _lib.check(lib.srx_bake_update(C.byref(a), stream))
+                lo = (ntex * 4 + 255) // 256 * 256 + 256
+                dist.all_reduce(self._workspace[lo:need].view(torch.int32), op=dist.ReduceOp.SUM, group=process_group)
+                a.phase = 3
+                _lib.check(lib.srx_bake_update(C.byref(a), stream))
+            elif sharded:
                 a.phase = 1
                 _lib.check(lib.srx_bake_update(C.byref(a), stream))
                 ntex = self.k * self.k * self.height * self.width

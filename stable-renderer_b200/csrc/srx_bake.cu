@@ -25,7 +25,8 @@ struct BakeGeom {
     int sprite, material, ignore_filter;
     int inverse_masks;
     int first_mode;
-    int frames_total;  // frames in this chunk
+    int frames_total;  // frames in this chunk (view-sharded bake: frames of ALL ranks)
+    unsigned int pix_offset;   // view-sharded bake: linear index of this rank's first pixel among all ranks' views, else 0
 };
 
 // mask and id tests of one pixel that is already in registers: true + its texel when the pixel takes part in the bake
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) k_bake_claim(const IdT *__restrict__ ids,
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
         long long tex;
         if (!bake_texel(ids, masks, i, g, false, &tex, status)) continue;
-        const unsigned int order1 = bake_order1((unsigned int)i, (unsigned int)hw, g);
+        const unsigned int order1 = bake_order1((unsigned int)i + g.pix_offset, (unsigned int)hw, g);
         if (tex == 0) { zmax = order1 > zmax ? order1 : zmax; continue; }
         if (g.first_mode && writtens[tex]) continue;
         // the owner word only grows: skip the atomic when a later pixel already claimed the texel (removes almost all
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) k_bake_claim_pair(const IdT *__restrict__
         for (int k = 0; k < 2 * NP; ++k) {
             t[k] = 0;
             ok[k] = bake_texel_eval(px[k], m[k], masks != nullptr, g, false, &t[k], status);
-            ord[k] = bake_order1((unsigned int)i0 + (unsigned int)k, hw, g);
+            ord[k] = bake_order1((unsigned int)i0 + (unsigned int)k + g.pix_offset, hw, g);
             if (ok[k] && t[k] == 0) { zmax = ord[k] > zmax ? ord[k] : zmax; ok[k] = false; }
             cur[k] = 0xffffffffu;
             if (ok[k]) cur[k] = __ldcg(owner + t[k]);
@@ -192,14 +193,17 @@ __global__ void __launch_bounds__(256) k_bake_write(const IdT *__restrict__ ids,
 template <typename CT>
 __global__ void __launch_bounds__(256) k_bake_write_texels(const CT *__restrict__ colors, uint8_t *__restrict__ writtens,
                                                             const unsigned int *__restrict__ owner, __half *__restrict__ values,
-                                                            BakeGeom g, long long ntex) {
+                                                            BakeGeom g, long long ntex, int frame_offset, int frames_local,
+                                                            int set_written) {
     const long long hw = (long long)g.H * g.W;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntex; t += (long long)gridDim.x * blockDim.x) {
         const unsigned int o = __ldcs(owner + t);
         if (o == 0u) continue;
         const long long order = (long long)o - 1;
         const long long fo = order / hw, pix = order - fo * hw;
-        const long long i = (g.first_mode ? (g.frames_total - 1 - fo) : fo) * hw + pix;
+        const long long fl = (g.first_mode ? (g.frames_total - 1 - fo) : fo) - frame_offset;   // frame among this rank's views
+        if (fl < 0 || fl >= frames_local) continue;                                          // another rank holds the winner
+        const long long i = fl * hw + pix;
         const CT *c = colors + i * g.Cin;
         __half *v = values + t * g.C;
         if (g.C == 4) {
@@ -210,6 +214,17 @@ __global__ void __launch_bounds__(256) k_bake_write_texels(const CT *__restrict_
         } else {
             for (int ch = 0; ch < g.C; ++ch) v[ch] = __float2half_rn(ch < g.Cin ? color_ld<CT>(c + ch) : 1.f);
         }
+        if (set_written) writtens[t] = 1;
+    }
+}
+
+// View-sharded bake, last step: texels claimed in this call take the winner's value (delta = the ranks' partial atlases summed
+// as int32 words: every texel is non-zero on exactly one rank, so the sum is that rank's bit pattern).
+__global__ void __launch_bounds__(256) k_bake_merge(const unsigned int *__restrict__ owner, const __half *__restrict__ delta,
+                                                     __half *__restrict__ values, uint8_t *__restrict__ writtens, long long ntex, int C) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntex; t += (long long)gridDim.x * blockDim.x) {
+        if (__ldcs(owner + t) == 0u) continue;
+        for (int ch = 0; ch < C; ++ch) values[t * C + ch] = delta[t * C + ch];
         writtens[t] = 1;
     }
 }
@@ -306,6 +321,11 @@ __global__ void __launch_bounds__(256) k_bake_finalize(const float *__restrict__
 // ---- host ------------------------------------------------------------------------------------------------------------
 static inline int64_t bk_align(int64_t v) { return (v + 255) / 256 * 256; }
 
+extern "C" int64_t srx_bake_sharded_workspace_bytes(int k2, int texels, int channels) {
+    const int64_t ntex = (int64_t)k2 * texels;
+    return bk_align(ntex * 4) + 256 + bk_align(ntex * channels * 2);
+}
+
 extern "C" int64_t srx_bake_workspace_bytes(int k2, int texels, int channels, int weight_mode) {
     (void)channels;
     const int64_t ntex = (int64_t)k2 * texels;
@@ -324,6 +344,7 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
     g.sprite = a->sprite_id; g.material = a->material_id; g.ignore_filter = a->ignore_obj_mat_id;
     g.inverse_masks = a->inverse_masks;
     g.first_mode = (a->mode == SRX_BAKE_FIRST || a->mode == SRX_BAKE_FIRST_AVG) ? 1 : 0;
+    g.pix_offset = 0u;
     const int sms = srx_sm_count_cached();
     const IdT *ids = reinterpret_cast<const IdT *>(a->ids_dev);
     const CT *colors = reinterpret_cast<const CT *>(a->colors_dev);
@@ -332,7 +353,49 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
     if (a->weight_mode == SRX_WEIGHT_NONE) {
         unsigned int *owner = reinterpret_cast<unsigned int *>(ws);
         status = reinterpret_cast<int *>(ws + bk_align(ntex * 4));
-        SRX_CUDA_CHECK(cudaMemsetAsync(status, 0, 256, st));
+        if (a->phase <= 1) SRX_CUDA_CHECK(cudaMemsetAsync(status, 0, 256, st));
+        if (a->phase != 0) {
+            // view-sharded bake of the reference modes: order keys number the views of ALL ranks, the owner words are
+            // MAX-reduced between phase 1 and 2, the ranks' partial atlases SUM-reduced (as int32 words) between phase 2 and 3
+            SRX_REQUIRE(a->frame_offset >= 0 && a->frames_global >= a->frame_offset + a->frames, SRX_ERR_INVALID,
+                        "frames_global must cover frame_offset + frames");
+            SRX_REQUIRE((long long)a->frames_global * hw < (1ll << 31), SRX_ERR_UNSUPPORTED,
+                        "view-sharded bake: all ranks' views together must stay below 2^31 pixels (order keys travel as int32)");
+            SRX_REQUIRE(a->workspace_bytes >= srx_bake_sharded_workspace_bytes(a->k2, a->texels, a->channels), SRX_ERR_INVALID, "workspace too small");
+            __half *delta = reinterpret_cast<__half *>(ws + bk_align(ntex * 4) + 256);
+            g.frames_total = a->frames_global;
+            g.pix_offset = (unsigned int)((long long)a->frame_offset * hw);
+            const long long npx = (long long)a->frames * hw;
+            long long nbt = (ntex + 255) / 256;
+            const int gridt = (int)(nbt < (long long)sms * 8 ? nbt : (long long)sms * 8);
+            if (a->phase == 1) {
+                SRX_CUDA_CHECK(cudaMemsetAsync(owner, 0, (size_t)ntex * 4, st));
+                long long nb = (npx + 255) / 256;
+                const int grid = (int)(nb < (long long)sms * 8 ? nb : (long long)sms * 8);
+                const bool pair_ok = (npx & 1) == 0 && (reinterpret_cast<uintptr_t>(ids) & 31) == 0 && (reinterpret_cast<uintptr_t>(a->masks_dev) & 7) == 0;
+                if (pair_ok) {
+                    long long nbp = (npx / 2 + 255) / 256;
+                    const int gridp = (int)(nbp < (long long)sms * 8 ? nbp : (long long)sms * 8);
+                    k_bake_claim_pair<IdT, 1><<<gridp, 256, 0, st>>>(ids, a->masks_dev, a->writtens_dev, owner, status, g, npx / 2);
+                } else {
+                    k_bake_claim<IdT><<<grid, 256, 0, st>>>(ids, a->masks_dev, a->writtens_dev, owner, status, g, npx);
+                }
+            } else if (a->phase == 2) {
+                SRX_CUDA_CHECK(cudaMemsetAsync(delta, 0, (size_t)bk_align(ntex * a->channels * 2), st));
+                k_bake_write_texels<CT><<<gridt, 256, 0, st>>>(colors, a->writtens_dev, owner, delta, g, ntex, a->frame_offset, a->frames, 0);
+            } else {
+                k_bake_merge<<<gridt, 256, 0, st>>>(owner, delta, values, a->writtens_dev, ntex, g.C);
+            }
+            SRX_CUDA_CHECK(cudaGetLastError());
+            if (a->phase != 1) return SRX_OK;      // the status word is written by the claim pass only
+            int st_claim = 0;
+            SRX_CUDA_CHECK(cudaMemcpyAsync(&st_claim, status, sizeof(int), cudaMemcpyDeviceToHost, st));
+            SRX_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (st_claim)
+                return srx_set_error(SRX_ERR_INDEX, "index out of range: a kept pixel addresses (map_index, vertexID) outside the "
+                                     "%d x %d atlas (corrmap.py:735)", a->k2, a->texels);
+            return SRX_OK;
+        }
         // the 32-bit order key holds frames_per_chunk*H*W + 1; longer sequences run as ordered chunks
         const long long max_frames = ((1ll << 32) - 2) / hw;
         SRX_REQUIRE(max_frames >= 1, SRX_ERR_UNSUPPORTED, "frame larger than 2^32 pixels");
@@ -357,7 +420,8 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
             if (npx * 2 >= ntex) {
                 long long nbt = (ntex + 255) / 256;
                 const int gridt = (int)(nbt < (long long)sms * 8 ? nbt : (long long)sms * 8);
-                k_bake_write_texels<CT><<<gridt, 256, 0, st>>>(colors + (long long)f0 * hw * g.Cin, a->writtens_dev, owner, values, g, ntex);
+                k_bake_write_texels<CT><<<gridt, 256, 0, st>>>(colors + (long long)f0 * hw * g.Cin, a->writtens_dev, owner, values, g, ntex,
+                                                               0, nf, 1);
             } else {
                 k_bake_write<IdT, CT><<<grid, 256, 0, st>>>(ids + (long long)f0 * hw, masks, colors + (long long)f0 * hw * g.Cin,
                                                             a->writtens_dev, owner, values, status, g, npx);
@@ -421,8 +485,8 @@ extern "C" int srx_bake_update(const srx_bake_args *a, void *stream) {
     SRX_REQUIRE(a->frames > 0 && a->height > 0 && a->width > 0 && a->color_channels > 0, SRX_ERR_INVALID, "non-positive dimension");
     SRX_REQUIRE(a->mode >= SRX_BAKE_REPLACE && a->mode <= SRX_BAKE_FIRST_AVG, SRX_ERR_INVALID, "unknown update mode");
     SRX_REQUIRE(a->weight_mode >= SRX_WEIGHT_NONE && a->weight_mode <= SRX_WEIGHT_VIEW_NORMAL_DEPTH, SRX_ERR_INVALID, "unknown weight mode");
-    SRX_REQUIRE(a->phase >= 0 && a->phase <= 2 && (a->phase == 0 || a->weight_mode != SRX_WEIGHT_NONE), SRX_ERR_INVALID,
-                "phase 1/2 exist for the weighted bake only");
+    SRX_REQUIRE(a->phase >= 0 && a->phase <= (a->weight_mode == SRX_WEIGHT_NONE ? 3 : 2), SRX_ERR_INVALID,
+                "phase must be 0..2 (weighted bake) or 0..3 (reference modes)");
     // channel fix-up (corrmap.py:681-684): truncate, or append alpha = 1 when C == 4 and the colour has 3 channels
     SRX_REQUIRE(a->color_channels >= a->channels || (a->channels == 4 && a->color_channels == 3), SRX_ERR_INVALID,
                 "shape mismatch: colour has %d channels, atlas has %d", a->color_channels, a->channels);

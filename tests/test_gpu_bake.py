@@ -214,3 +214,39 @@ def test_bake_without_masks_background_goes_to_texel_zero(shape, mode):
     v, w = _atlas(cm)
     assert w[0, 0] and np.array_equal(w, writtens)
     assert np.array_equal(v, values.view(np.uint16))
+
+
+@pytest.mark.parametrize("mode", ["replace", "first"])
+def test_reference_mode_bake_sharded_phases_equal_single_bake(mode):
+    """View-sharded bake of the reference modes emulated on one GPU: three 'ranks' hold 2 + 3 + 1 views; claim
+    with order keys over all views (phase 1), MAX of the owner words (the all-reduce), each rank writes the texels its views won
+    (phase 2), SUM of the partial atlases as int32 words, merge (phase 3) -> bit for bit the atlas of one bake over all views.
+    Run twice, so that `first` has to respect texels written by the first round."""
+    import torch
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import CorrespondMap
+    F, H, tex, k = 6, 64, 48, 2
+    cuts = [(0, 2), (2, 5), (5, 6)]
+    ntex = k * k * tex * tex
+    ref = CorrespondMap(name="ref", k=k, height=tex, width=tex, channel_count=4)
+    parts = [CorrespondMap(name=f"p{r}", k=k, height=tex, width=tex, channel_count=4) for r in range(len(cuts))]
+    for rnd in range(2):
+        ids = synthetic.make_ids(F, H, H, tex_h=tex, tex_w=tex, k=k, frac_2048=0.0, seed=40 + rnd, frame_offset=3 * rnd).cuda()
+        colors = synthetic.make_colors(F, H, H, 3, seed=41 + rnd).cuda()
+        kw = dict(mode=mode, ignore_obj_mat_id=True)
+        ref.update(colors, ids, **kw)
+        sh = dict(frames_global=F, **kw)
+        for (lo, hi), cm in zip(cuts, parts):
+            cm.update(colors[lo:hi], ids[lo:hi], phase=1, frame_offset=lo, **sh)
+        owner = torch.stack([cm._workspace[:ntex * 4].view(torch.int32) for cm in parts]).amax(dim=0)
+        for (lo, hi), cm in zip(cuts, parts):
+            cm._workspace[:ntex * 4].view(torch.int32).copy_(owner)
+            cm.update(colors[lo:hi], ids[lo:hi], phase=2, frame_offset=lo, **sh)
+        a0 = (ntex * 4 + 255) // 256 * 256 + 256
+        n = parts[0]._workspace.numel()
+        delta = torch.stack([cm._workspace[a0:n].view(torch.int32) for cm in parts]).sum(dim=0, dtype=torch.int32)
+        for (lo, hi), cm in zip(cuts, parts):
+            cm._workspace[a0:n].view(torch.int32).copy_(delta)
+            cm.update(colors[lo:hi], ids[lo:hi], phase=3, frame_offset=lo, **sh)
+            assert torch.equal(cm._writtens, ref._writtens), (mode, rnd)
+            assert torch.equal(cm._values.view(torch.int16), ref._values.view(torch.int16)), (mode, rnd)
