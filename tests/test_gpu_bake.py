@@ -250,3 +250,17 @@ def test_reference_mode_bake_sharded_phases_equal_single_bake(mode):
             cm.update(colors[lo:hi], ids[lo:hi], phase=3, frame_offset=lo, **sh)
             assert torch.equal(cm._writtens, ref._writtens), (mode, rnd)
             assert torch.equal(cm._values.view(torch.int16), ref._values.view(torch.int16)), (mode, rnd)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_view_sharded_bake_two_gpus():
+    """Real view-sharded bakes over NCCL: reference modes bit exact, weighted bake within an fp16 ulp (tests/mp_bake_worker.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tests", "mp_bake_worker.py")]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
+    assert "BAKE_SHARD_OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
