@@ -11,10 +11,15 @@ two metrics that adds up over GPUs; `overlap_steps_per_sec` is reported beside i
 A "step" is one full `OverlapCorresponder.step_finished` on ids that are NEW for the step (streaming regime,
 SURVEY.md §8d): key the id buffers, segment-reduce the latents per key, [all-reduce the key-indexed accumulator
 when frames are sharded], gather/blend, AdaIN, in place.  Workloads (BASELINE.json configs):
-    cfg1  16 frames  512^2 ids,  64x64x4 f32          cfg2  32 frames/GPU 512^2, 64x64x4 f32   (default, weak scaling)
-    cfg3  96 frames 1024^2 ids, 128x128x4 bf16, frames sharded over the GPUs (strong scaling)
+    cfg1  16 frames  512^2 ids,  64x64x4 f32          cfg2  32 frames/GPU 512^2, 64x64x4 f32   (weak scaling)
+    cfg3  96 frames 1024^2 ids, 128x128x4 bf16, frames sharded over the GPUs (strong scaling) — the DEFAULT: the config
+          BASELINE.json's north_star target is quoted on; it fits one GPU, so N = 1/2/4/8 all run this named config
     cfg5  768 frames 512^2, 64x64x4 f32, 4 objects, sharded (strong scaling)
     bake  cfg4: 64 views 1024^2 RGB -> 4096^2 atlas, depth/normal weighted, views sharded (metric: views/s)
+
+The default run also carries, in the same JSON line: `parity_check` (a small N-rank step through the same exchange path
+checked against oracle/srx_oracle.py — the run exits non-zero when it fails), and `extra.cfg2` (streaming step, cached-plan
+step and the 20-step job of BASELINE config 2) and, at N = 1, `extra.cfg4_bake` (BASELINE config 4).
 
 Rank 0 prints ONE JSON line.  `value` is device-timed with inputs resident in HBM (CUDA events around exactly K
 steps replayed from a CUDA graph, max over ranks); `e2e` goes through the public API with host buffers (pinned H2D of
@@ -172,7 +177,81 @@ def shard(frames_total: int, scaling: str, rank: int, world: int):
     return count, first, frames_total
 
 
-def run_overlap(args, rank: int, local: int, world: int) -> dict:
+def workload_string(workload: str, frames_total: int) -> str:
+    """`config.workload` — identical in our arm and in the reference arm."""
+    _, H, h, dtype, _, _, _ = WORKLOADS[workload]
+    return (f"{workload}: {frames_total} frames of {H}x{H}x4 int32 ids -> {h}x{h}x4 {DTYPE_NAME[dtype]} latents, "
+            f"ratio {RATIO}, one overlap step per id batch pass (streaming regime)")
+
+
+def percentile(v, q):
+    s = sorted(v)
+    return s[min(len(s) - 1, max(0, int(math.ceil(q * len(s))) - 1))]
+
+
+def parity_check(rank: int, local: int, world: int, exchange: str, dtype: torch.dtype) -> dict:
+    """A small N-rank overlap step (ragged frame shards, same exchange path as the timed run, streaming AND cached-plan
+    regime) checked against the numpy oracle.  Outside every timed region.  oracle/ is used here as the checker only."""
+    import numpy as np
+    import torch.distributed as dist
+    import srx_oracle as O
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.plan import OverlapPlan
+    from stable_renderer_b200.sharding import frame_shard
+    dev = torch.device("cuda", local)
+    frames_total, H, h, tex = (2 * world + 1 if world > 1 else 5), 128, 16, 64
+    ids = synthetic.make_ids(frames_total, H, H, tex_h=tex, tex_w=tex, frac_2048=0.05, seed=77)
+    first, count = frame_shard(frames_total, rank, world)
+    res = {"frames_total": frames_total, "regimes": ["streaming", "cached_plan"]}
+    ok_all = True
+    for dt, name in ((torch.float32, "f32"),) + (((dtype, DTYPE_NAME[dtype]),) if dtype != torch.float32 else ()):
+        x0 = synthetic.make_latents(frames_total, 4, h, h, seed=3, dtype=dt)
+        want = O.overlap_step(x0.float().numpy(), ids.numpy(), None, ratio=RATIO, accumulate="f64")[first:first + count]
+        ids_dev = ids[first:first + count].contiguous().to(dev)
+        plan = OverlapPlan(None, (count, 4, h, h), id_shape=ids_dev.shape, id_dtype=ids_dev.dtype, key_capacity=tex * tex,
+                           device=dev, process_group=dist.group.WORLD if world > 1 else None, exchange=exchange)
+        errs = []
+        for regime in ("streaming", "cached_plan"):
+            x = x0[first:first + count].contiguous().to(dev)
+            if regime == "streaming":
+                if world == 1 or plan.exchange == "peer":
+                    plan.step(x, RATIO, ids=ids_dev)
+                else:
+                    plan.reduce(x, ids=ids_dev)
+                    dist.all_reduce(plan.accumulator, op=dist.ReduceOp.SUM)
+                    plan.gather(x, RATIO)
+            else:
+                if not (plan.fused and (world == 1 or plan.exchange == "peer")):
+                    continue
+                plan.build_cache(ids_dev)
+                plan.step(x, RATIO, cached=True)
+            plan.check()
+            got = x.float().cpu().numpy()
+            err = np.abs(got - want)
+            # f32: 1e-5 relative (north_star) with an absolute floor for values near zero; 16-bit latents: 1e-2
+            tol = (3e-6 + 1e-5 * np.abs(want)) if dt == torch.float32 else 1e-2 * np.maximum(1.0, np.abs(want))
+            errs.append(float(err.max()))
+            ok_all = ok_all and bool((err <= tol).all()) and bool(np.isfinite(got).all())
+        plan.close()
+        res[f"max_abs_err_{name}"] = max(errs)
+    t = torch.tensor([max(v for k, v in res.items() if k.startswith("max_abs_err")), 0.0 if ok_all else 1.0],
+                     dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for k in [k for k in res if k.startswith("max_abs_err")]:
+            tk = torch.tensor([res[k]], dtype=torch.float64, device=dev)
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+            res[k] = float(tk.item())
+    res["max_abs_err"] = float(t[0].item())
+    res["ok"] = bool(t[1].item() == 0.0)
+    res["ranks"] = world
+    res["checker"] = "oracle/srx_oracle.py::overlap_step (float64 accumulation)"
+    res["tolerance"] = "f32: 3e-6 + 1e-5*|ref|; f16/bf16: 1e-2*max(1,|ref|)"
+    return res
+
+
+def run_overlap(args, workload: str, rank: int, local: int, world: int, light: bool = False) -> dict:
+    """light=True: the secondary record of another named config (fewer repetitions, no every-step-new-ids e2e)."""
     import torch.distributed as dist
     from stable_renderer_b200 import _lib, synthetic
     from stable_renderer_b200.corresponder import OverlapCorresponder
@@ -180,7 +259,7 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
     from stable_renderer_b200.plan import OverlapPlan
 
     _lib.load()  # no extension, no benchmark
-    frames_cfg, H, h, dtype, tex, n_obj, scaling = WORKLOADS[args.workload]
+    frames_cfg, H, h, dtype, tex, n_obj, scaling = WORKLOADS[workload]
     F, f0, F_global = shard(frames_cfg, scaling, rank, world)
     dev = torch.device("cuda", local)
     key_capacity = tex * tex            # = CorrespondMap height*width: what the engine knows about the key space
@@ -190,7 +269,8 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
     ids0 = synthetic.make_ids(F, H, H, tex_h=tex, tex_w=tex, n_obj=n_obj, frac_2048=0.05, seed=1234, device=dev,
                               frame_offset=f0)
     id_bytes = ids0.numel() * 4
-    n_rot = 3 if id_bytes < (400 << 20) else 2      # rotate id buffers so that no step finds its ids in the 126 MB L2
+    # rotate id buffers so that no step finds its ids in the 126 MB L2 (one buffer of >= 400 MB is "larger than L2" by itself)
+    n_rot = 3 if id_bytes < (200 << 20) else 2 if id_bytes < (400 << 20) else 1
     ids_rot = [ids0] + [torch.roll(ids0, shifts=r, dims=0).contiguous() for r in range(1, n_rot)]
     x = synthetic.make_latents(F_global, 4, h, h, seed=0, dtype=dtype)[f0:f0 + F].contiguous().to(dev)
     x_init = x.clone()
@@ -202,65 +282,74 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
 
     def one_step(r: int):
         if world == 1 or peer:
-            plan.step(x, RATIO, ids=ids_rot[r])      # one persistent kernel (exchange over NVLink inside it when sharded)
+            plan.step(x, RATIO, ids=ids_rot[r % n_rot])   # one persistent kernel (exchange over NVLink inside it when sharded)
         else:
-            plan.reduce(x, ids=ids_rot[r])
+            plan.reduce(x, ids=ids_rot[r % n_rot])
             dist.all_reduce(acc, op=dist.ReduceOp.SUM)
             plan.gather(x, RATIO)
 
-    # ---- CUDA graph of n_rot consecutive steps -------------------------------------------------------------------
+    # ---- CUDA graphs holding EXACTLY K steps: q replays of an m-step graph + one r-step graph, no eager launch ------
     launch_mode = "cuda_graph"
-    graph = None
+    m = min(K, 48)
+    if n_rot > 1 and m >= n_rot:
+        m -= m % n_rot
+    q, r_rem = divmod(K, m)
+    graphs = []
     side = torch.cuda.Stream(device=dev)
     try:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for r in range(n_rot):
+            for r in range(max(n_rot, 2)):
                 one_step(r)                         # warm everything outside capture (NCCL channels, occupancy queries)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            for r in range(n_rot):
-                one_step(r)
+        for n_steps in (m, r_rem):
+            if n_steps == 0:
+                graphs.append(None)
+                continue
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for r in range(n_steps):
+                    one_step(r)
+            graphs.append(g)
         torch.cuda.synchronize()
     except Exception as e:
         log(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); falling back to eager launches")
-        graph = None
+        graphs = []
         launch_mode = "eager"
         torch.cuda.synchronize()
 
-    def run_steps(n: int):
-        if graph is not None:
-            full, rem = divmod(n, n_rot)
-            for _ in range(full):
-                graph.replay()
-            for r in range(rem):
-                one_step(r)
+    def run_k_steps():
+        if graphs:
+            for _ in range(q):
+                graphs[0].replay()
+            if graphs[1] is not None:
+                graphs[1].replay()
         else:
-            for i in range(n):
-                one_step(i % n_rot)
+            for i in range(K):
+                one_step(i)
 
     sampler = ClockSampler(local)
     x.copy_(x_init)
-    run_steps(Wm)
+    for i in range(Wm):
+        one_step(i)
+    if graphs:
+        graphs[0].replay()                              # graph warm-up (first replay uploads the graph)
     barrier(world)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    run_steps(K)
+    run_k_steps()
     ev1.record()
     torch.cuda.synchronize()
     barrier(world)
     ms_total = max_over_ranks(ev0.elapsed_time(ev1), world)
     ms_step = ms_total / K
-    clocks = sampler.stop()        # clocks are sampled during the timed region of `value`; NVML polling would only
-                                   # perturb the host-driven end-to-end loops below
     plan.check()
     assert torch.isfinite(x.float()).all(), "latents became non-finite"
 
     # ---- dominant kernel alone, per-launch CUDA events (eager launches on the current stream) ----------------------
-    n_k1 = min(K, 200)
+    n_k1 = min(K, 200 if not light else 50)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k1)]
     elem = x.element_size()
     step_bytes = 16 * F * H * H + 2 * F * 4 * h * h * elem           # SURVEY.md §8d streaming-regime figure, per GPU
@@ -285,6 +374,8 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
         b.record()
     torch.cuda.synchronize()
     k1_ms_eager = max_over_ranks(statistics.mean([a.elapsed_time(b) for a, b in evs]), world)
+    clocks = sampler.stop()        # clocks are sampled during the device-timed regions; NVML polling would only
+                                   # perturb the host-driven end-to-end loops below
     k1_ms = k1_ms_eager
     if fused_kernel:
         # one launch per step: the kernel's average launch duration over the timed region IS the step time
@@ -342,14 +433,16 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
         job_ms = max_over_ranks(max(j0.elapsed_time(j1), tw), world) / n_jobs
         for pj in plans[1:]:
             pj.close()
+        cached_alg = 2 * F * 4 * h * h * elem + 8 * seen + 4 * F * h * h
         cached = {"ms_per_step": cached_ms, "steps_per_sec": 1e3 / cached_ms,
                   "latent_px_per_sec": F_global * h * h * 1e3 / cached_ms,
                   "job": {"steps": job_steps, "ms": job_ms, "steps_per_sec": job_steps * 1e3 / job_ms,
                           "latent_px_per_sec": F_global * h * h * job_steps * 1e3 / job_ms,
-                          "includes": "bucketing pass on fresh ids (2 id passes, 1 host sync) + 20 cached steps, eager launches"},
+                          "includes": "bucketing pass on fresh ids (2 id passes) + 20 cached steps, eager launches"},
                   "pairs_kept_per_gpu": kept, "pairs_seen_per_gpu": seen,
-                  "algorithmic_bytes_per_step": 2 * F * 4 * h * h * elem + 8 * seen + 4 * F * h * h,
+                  "algorithmic_bytes_per_step": cached_alg,
                   "traffic_bytes_per_step": 2 * F * 4 * h * h * elem + 8 * kept + 4 * F * h * h,
+                  "roofline_frac": cached_alg / (cached_ms * 1e-3) / 1e9 / peak,
                   "l2": f"{n_jobs} independent runs of {per_job >> 20} MiB each stepped round-robin: no step finds its pool, "
                         f"latents or accumulators in the 126 MB L2",
                   "note": "ids unchanged between the steps of a run (SURVEY.md 8d cached-plan regime)"}
@@ -370,50 +463,55 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
     x_out = torch.empty_like(x_host).pin_memory()
     ids_dev = torch.empty_like(ids0)
     x_dev = torch.empty_like(x)
-    idm = IDMap(tensor=ids_dev, masks=torch.zeros(1, 1, 1))        # masks are not used by the overlap step
-    ed = _ED()
-    ed.id_maps, ed.correspond_maps = idm, {(1, 0): _MapSize()}
-    ctx = _Ctx()
-    ctx.noise, ctx.timestep = x_dev, 900
-    oc = OverlapCorresponder(step_finished_inject_ratio=RATIO, process_group=True if world > 1 else None,
-                             exchange=args.exchange, cache_plan=False)   # every e2e step brings new ids
-    n_e2e = max(10, min(K, 200))
 
-    def e2e_step(i: int):
-        ids_dev.copy_(ids_host[i % n_rot], non_blocking=True)
-        x_dev.copy_(x_host, non_blocking=True)
-        oc.step_finished(ed, ctx)
-        x_out.copy_(x_dev, non_blocking=True)
+    e2e_stream = None
+    if not light:
+        idm = IDMap(tensor=ids_dev, masks=torch.zeros(1, 1, 1))        # masks are not used by the overlap step
+        ed = _ED()
+        ed.id_maps, ed.correspond_maps = idm, {(1, 0): _MapSize()}
+        ctx = _Ctx()
+        ctx.noise, ctx.timestep = x_dev, 900
+        oc = OverlapCorresponder(step_finished_inject_ratio=RATIO, process_group=True if world > 1 else None,
+                                 exchange=args.exchange, cache_plan=False)   # every e2e step brings new ids
+        n_e2e = max(10, min(K, 200)) if id_bytes < (400 << 20) else 10
 
-    for i in range(3):
-        e2e_step(i)
-    barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall = time.perf_counter()
-    e0.record()
-    for i in range(n_e2e):
-        e2e_step(i)
-    e1.record()
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall
-    barrier(world)
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), t_wall * 1e3), world) / n_e2e
-    e2e_stream = {"value": F_global * h * h * 1e3 / e2e_ms, "unit": "latent-px/s",
-                  "h2d_bytes_per_step": id_bytes + x.numel() * elem, "d2h_bytes_per_step": x.numel() * elem,
-                  "ms_per_step": e2e_ms, "steps_per_sec": 1e3 / e2e_ms, "steps": n_e2e,
-                  "api": "OverlapCorresponder.step_finished(engine_data, sampling_context)",
-                  "regime": "every step brings a new id batch over PCIe (PCIe bound)"}
+        def e2e_step(i: int):
+            ids_dev.copy_(ids_host[i % n_rot], non_blocking=True)
+            x_dev.copy_(x_host, non_blocking=True)
+            oc.step_finished(ed, ctx)
+            x_out.copy_(x_dev, non_blocking=True)
+
+        for i in range(3):
+            e2e_step(i)
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        e0.record()
+        for i in range(n_e2e):
+            e2e_step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall
+        barrier(world)
+        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), t_wall * 1e3), world) / n_e2e
+        e2e_stream = {"value": F_global * h * h * 1e3 / e2e_ms, "unit": "latent-px/s",
+                      "h2d_bytes_per_step": id_bytes + x.numel() * elem, "d2h_bytes_per_step": x.numel() * elem,
+                      "ms_per_step": e2e_ms, "steps_per_sec": 1e3 / e2e_ms, "steps": n_e2e,
+                      "api": "OverlapCorresponder.step_finished(engine_data, sampling_context)",
+                      "regime": "every step brings a new id batch over PCIe (PCIe bound)"}
 
     # The named config: one sampling run = one id batch + 20 denoise steps.  Per run the ids cross PCIe once; every step
     # copies its latents in, calls step_finished (which buckets the ids on the first step and then runs from the cached
     # plan) and copies the latents out.  This is also how the reference arm is timed (keying cached per id batch).
+    # Every run is timed on its own (wall clock around a synchronize); the value is the MEDIAN run, p90 beside it.
     e2e_job = None
     if fused_kernel:
-        job_steps, n_jobs = 20, 8
+        job_steps = 20
+        n_runs = 50 if not light else 30
         oc2 = OverlapCorresponder(step_finished_inject_ratio=RATIO, process_group=True if world > 1 else None,
                                   exchange=args.exchange, cache_plan=True)
-        # (uploading the next run's ids on a copy stream while this run steps was tried: the 128 MiB copy and the per-step
-        # latent copies then share the DMA engine chunk by chunk and a run takes 4.7 or 13 ms at random; sequential it is)
+        # (uploading the next run's ids on a copy stream while this run steps was tried: the id copy and the per-step
+        # latent copies then share the DMA engine chunk by chunk and run times become bimodal; sequential it is)
         idm2 = IDMap(tensor=ids_dev, masks=torch.zeros(1, 1, 1))
         ed2 = _ED()
         ed2.id_maps, ed2.correspond_maps = idm2, {(1, 0): _MapSize()}
@@ -429,34 +527,43 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
                 oc2.step_finished(ed2, ctx2)
                 x_out.copy_(x_dev, non_blocking=True)
 
-        e2e_job_run(0)
-        torch.cuda.synchronize()
-        barrier(world)
-        t_wall = time.perf_counter()
-        for j in range(n_jobs):
+        for j in range(2):
             e2e_job_run(j)
         torch.cuda.synchronize()
-        t_wall = (time.perf_counter() - t_wall) * 1e3
-        barrier(world)
-        job_ms = max_over_ranks(t_wall, world) / n_jobs
+        run_ms = []
+        for j in range(n_runs):
+            barrier(world)
+            t_wall = time.perf_counter()
+            e2e_job_run(j)
+            torch.cuda.synchronize()
+            run_ms.append((time.perf_counter() - t_wall) * 1e3)
+        if world > 1:
+            tr = torch.tensor(run_ms, dtype=torch.float64, device=dev)
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+            run_ms = [float(v) for v in tr.cpu()]
+        job_ms = statistics.median(run_ms)
         e2e_job = {"value": F_global * h * h * job_steps * 1e3 / job_ms, "unit": "latent-px/s",
                    "steps_per_sec": job_steps * 1e3 / job_ms, "ms_per_step": job_ms / job_steps, "ms_per_run": job_ms,
-                   "steps": job_steps * n_jobs,
+                   "ms_per_run_p90": percentile(run_ms, 0.9), "ms_per_run_mean": statistics.mean(run_ms),
+                   "ms_per_run_min": min(run_ms), "runs": n_runs, "steps": job_steps * n_runs,
                    "h2d_bytes_per_step": id_bytes // job_steps + x.numel() * elem, "d2h_bytes_per_step": x.numel() * elem,
                    "api": "OverlapCorresponder.step_finished(engine_data, sampling_context)",
                    "regime": f"runs of {job_steps} denoise steps on one id batch: ids H2D once per run ({id_bytes >> 20} MiB, "
-                             "amortised above), latents H2D + D2H every step; wall clock over all runs"}
+                             "amortised above), latents H2D + D2H every step; median over the runs, each timed on the wall "
+                             "clock (max over ranks)"}
 
     out = {
         "metric": "overlap_latent_px_per_sec", "value": F_global * h * h * 1e3 / ms_step, "unit": "latent-px/s",
         "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": DTYPE_NAME[dtype], "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {F_global} frames of {H}x{H}x4 int32 ids -> {h}x{h}x4 "
-                               f"{DTYPE_NAME[dtype]} latents, ratio {RATIO}, streaming regime (ids new every step)",
+        "config": {"workload": workload_string(workload, F_global),
                    "frames_per_gpu": F, "frames_total": F_global, "key_capacity": key_capacity,
-                   "launch": launch_mode, "fast_path": bool(plan.fast_path),
-                   "l2": f"{n_rot} id buffers of {id_bytes >> 20} MiB rotate, so no step finds its ids in the 126 MB L2",
+                   "launch": launch_mode + (f" ({q} replays of a {m}-step graph" + (f" + one {r_rem}-step graph" if r_rem else "")
+                                            + ", no eager launch in the timed region)" if graphs else ""),
+                   "fast_path": bool(plan.fast_path),
+                   "l2": (f"{n_rot} id buffers of {id_bytes >> 20} MiB rotate, so no step finds its ids in the 126 MB L2" if n_rot > 1
+                          else f"the ids of one step ({id_bytes >> 20} MiB per GPU) are larger than the 126 MB L2"),
                    "kernels": "one persistent kernel per step" if fused_kernel else "split reduce / gather kernels",
                    "parallelism": (f"frames sharded over {world} GPU(s), key accumulator ({acc.numel() * 4 >> 10} KiB) "
                                    + ("exchanged inside the step kernel over NVLink peer memory (reduce-scatter + all-gather)"
@@ -473,12 +580,16 @@ def run_overlap(args, rank: int, local: int, world: int) -> dict:
         "gpu_launches": K if fused_kernel else (2 * K if plan.fast_path else 3 * K),
         "roofline": {"bound": "hbm", "kernel": k1_name,
                      "achieved": k1_gbs, "peak": peak, "unit": "GB/s", "frac": k1_gbs / peak,
-                     "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                     "traffic": ncu_traffic(workload), "peak_source": peak_src,
                      "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms, "ms_per_launch_eager_events": k1_ms_eager,
                      "step_bytes_per_gpu": step_bytes,
+                     "aggregate": {"bytes_per_step": step_bytes * world if scaling == "weak" else
+                                   16 * F_global * H * H + 2 * F_global * 4 * h * h * elem,
+                                   "peak": peak * world, "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
                      "step_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
     }
     plan.close()
+    del ids_rot, ids_host, ids_dev, ids0
     return out
 
 
@@ -673,12 +784,14 @@ def cpu_bake_baseline(views: int = 4) -> dict:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=list(WORKLOADS) + ["bake", "legacy"], default="cfg2")
+    ap.add_argument("--workload", choices=list(WORKLOADS) + ["bake", "legacy"], default="cfg3")
     ap.add_argument("--bake-weight", default="view_normal_depth", choices=["none", "uniform", "view_normal", "view_normal_depth"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary records (extra.cfg2, extra.cfg4_bake) of the default run")
     ap.add_argument("--exchange", choices=["auto", "peer", "nccl"], default="auto",
                     help="multi-GPU accumulator exchange: inside the step kernel over NVLink peer memory, or NCCL all-reduce")
     ap.add_argument("--split-kernels", action="store_true", help="run the split reduce / gather kernels instead of the persistent one")
@@ -689,7 +802,7 @@ def main():
         # the reference's own CPU path for this metric/config; rank 0 alone runs it
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        wl = "cfg2" if args.workload in ("bake", "legacy") else args.workload
+        wl = "cfg3" if args.workload in ("bake", "legacy") else args.workload
         frames_cfg, H, h, dtype, tex, n_obj, scaling = WORKLOADS[wl]
         # bounded sample: enough frames per step that K + W steps end within ~2 minutes
         probe = cpu_overlap_baseline(wl, budget_s=2.0, max_steps=3, frames_cap=2)
@@ -704,8 +817,9 @@ def main():
                 "overlap_steps_per_sec": steps_per_sec,
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / steps_per_sec,
                 "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{wl}: {frames_total} frames of {H}x{H}x4 int32 ids -> {h}x{h}x4 latents, "
-                                       f"ratio {RATIO}; reference CPU torch path (keying cached per id batch as the reference does)"},
+                "config": {"workload": workload_string(wl, frames_total),
+                           "arm": "reference CPU torch path (oracle/torch_port.py: the reference's torch ops, keying cached per id "
+                                  "batch as the reference does; float32 arithmetic on the same latents)"},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": value, "unit": "latent-px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -716,12 +830,37 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU baseline")
     rank, local, world = init_dist(args.gpus)
+    t_start = time.perf_counter()
+    parity = None
     if args.workload == "bake":
         out = run_bake(args, rank, local, world)
     elif args.workload == "legacy":
         out = run_legacy(args, rank, local, world)
     else:
-        out = run_overlap(args, rank, local, world)
+        # N-rank parity step first (outside every timed region): a wrong answer must not produce a bench line
+        parity = parity_check(rank, local, world, args.exchange, WORKLOADS[args.workload][3])
+        out = run_overlap(args, args.workload, rank, local, world)
+        out["parity_check"] = parity
+        if not args.no_extras:
+            extra = {}
+            torch.cuda.empty_cache()
+            if args.workload != "cfg2":
+                a2 = argparse.Namespace(**vars(args))
+                a2.steps, a2.warmup = max(60, min(args.steps, 600)), max(args.warmup, 5)
+                r2 = run_overlap(a2, "cfg2", rank, local, world, light=True)
+                extra["cfg2"] = {k: r2[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "overlap_steps_per_sec",
+                                                    "config", "roofline", "cached_plan", "e2e", "dtype")}
+                torch.cuda.empty_cache()
+            if world == 1:
+                a4 = argparse.Namespace(**vars(args))
+                a4.steps, a4.warmup = max(10, min(args.steps, 50)), 3
+                for wname, key in (("view_normal_depth", "cfg4_bake"), ("none", "cfg4_bake_reference_modes")):
+                    a4.bake_weight = wname
+                    r4 = run_bake(a4, rank, local, world)
+                    extra[key] = {k: r4[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "config", "roofline", "e2e",
+                                                     "texels_per_sec", "dtype")}
+                    torch.cuda.empty_cache()
+            out["extra"] = extra
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline and args.workload == "bake":
             out["cpu_baseline"] = cpu_bake_baseline()
@@ -729,12 +868,16 @@ def main():
             out["cpu_baseline"] = cpu_legacy_baseline()
         if world == 1 and not args.no_cpu_baseline and args.workload not in ("bake", "legacy"):
             out["cpu_baseline"] = cpu_overlap_baseline(args.workload, budget_s=12.0, max_steps=40,
-                                                       frames_cap=32 if args.workload in ("cfg3", "cfg5") else None)
+                                                       frames_cap=16 if args.workload in ("cfg3", "cfg5") else None)
+        out["bench_wall_s"] = time.perf_counter() - t_start
         print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        log(f"[bench] PARITY CHECK FAILED: {parity}")
+        sys.exit(3)
 
 
 if __name__ == "__main__":
