@@ -33,7 +33,8 @@ typedef enum srx_status {
     SRX_ERR_INDEX = -2,       /* an entry addresses a latent cell / texel out of range (maps to IndexError) */
     SRX_ERR_CUDA = -3,        /* CUDA runtime error */
     SRX_ERR_UNSUPPORTED = -4, /* valid request that this build does not implement */
-    SRX_ERR_KEY_RANGE = -5    /* key outside the dense slot table */
+    SRX_ERR_KEY_RANGE = -5,   /* key outside the dense slot table */
+    SRX_ERR_PEER_LOST = -6    /* a bounded wait inside the frame-sharded step kernel timed out (srx_plan_check) */
 } srx_status;
 
 typedef enum srx_dtype {
@@ -338,6 +339,18 @@ int srx_gl_unregister(srx_gl_resource *res);
 int srx_array_to_tensor(void *cuda_array, void *dst_dev, int width, int height, int texel_bytes, int flip, void *stream);
 int srx_tensor_to_array(void *cuda_array, const void *src_dev, int width, int height, int texel_bytes, int flip,
                         int x_offset, int y_offset, void *stream);
+/* Channel-aware forms for the Texture wrapper (texture.py:221-254, 326-408): the array's own channel count decides how texels
+ * are read / written — a three-channel GL texture is a four-channel CUDA array.  array -> tensor [height,width,dst_channels]
+ * drops extra array channels; tensor [height,width,src_channels] -> array region pads RGB with alpha = 1 (`one_bits` = the value
+ * 1 in the element type, texture.py:379-380), repeats a single channel (:377-378) and truncates wider data (:383-384). */
+int srx_array_to_tensor_ch(void *cuda_array, void *dst_dev, int width, int height, int elem_bytes, int dst_channels, int flip, void *stream);
+int srx_tensor_to_array_ch(void *cuda_array, const void *src_dev, int width, int height, int elem_bytes, int src_channels, int flip,
+                           int x_offset, int y_offset, unsigned int one_bits, void *stream);
+/* CorrespondMap.load (corrmap.py:443-489) without the host round trip: layer <- fp16 atlas [height*width, channels];
+ * transpose = 1 reproduces the reference's `get_map(i, order='whc')` upload: texel (x, y) = values[x * width + y]. */
+int srx_atlas_to_array(void *cuda_array, const void *values_dev, int height, int width, int channels, int transpose, void *stream);
+/* cudaArray of layer `layer` of a mapped GL_TEXTURE_2D_ARRAY resource */
+int srx_gl_mapped_layer(srx_gl_resource *res, int layer, void **cuda_array_out);
 /* test helpers: plain cudaArray allocation so that the copy kernels can be exercised without a GL context */
 int srx_array_alloc(void **cuda_array_out, int width, int height, int channels, int bits_per_channel, int kind /*0 sint,1 uint,2 float*/);
 int srx_array_free(void *cuda_array);
@@ -387,6 +400,23 @@ typedef struct srx_gbuffer_temp {   /* RenderManager._*_buffer_temp (renderManag
     void *noise;               /* fp16 [H,W,4] */
     void *canny;               /* fp16 [H,W,3] */
 } srx_gbuffer_temp;
+/* The same attachments as mapped cudaArrays (cudaArray_t from srx_gl_map; NULL = absent): the zero-copy form of the ingest —
+ * the kernels read the texture memory through surface objects, nothing is staged (replaces the seven Texture.tensor() read-backs
+ * of renderManager.py:882-943: map, Memcpy2D, torch.cuda.synchronize(), flip, clone).  CUDA arrays hold 1, 2 or 4 channels:
+ * position / canny (RGB32F in GL, renderManager.py:268,352) are four-channel arrays whose last channel is ignored. */
+typedef struct srx_gbuffer_arrays {
+    void *color;               /* RGBA16F */
+    void *ids;                 /* RGBA32I */
+    void *pos;                 /* RGBA32F (xyz used) */
+    void *normal_depth;        /* RGBA16F */
+    void *noise;               /* RGBA16F */
+    void *canny;               /* RGBA32F or RGBA16F (xyz used) */
+    int canny_dtype;           /* SRX_F32 | SRX_F16; canny_maps has the same dtype */
+} srx_gbuffer_arrays;
+/* srx_frame_ingest with `arrays` as the source (args->src is ignored). */
+int srx_frame_ingest_arrays(const srx_ingest_args *args, const srx_gbuffer_arrays *arrays, void *stream);
+int srx_gbuffer_merge_closer_arrays(const srx_gbuffer_arrays *cur, int height, int width, int flip_rows, const srx_gbuffer_temp *temp,
+                                    void *stream);
 /* Where cur's reversed depth > temp->depth, every attachment of the pixel replaces the stored one (in place). */
 int srx_gbuffer_merge_closer(const srx_gbuffer *cur, int height, int width, int flip_rows, const srx_gbuffer_temp *temp, void *stream);
 

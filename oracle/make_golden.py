@@ -419,6 +419,50 @@ def ingest_cases(R):
     save("frame_ingest", **out)
 
 
+def node_cases():
+    """The reference's node classes (legacy StableRenderSampler / OverlapScheduler, current CorrespondSampler + OverlapCorresponder
+    node) driven by the scripted sampler of tests/helpers.py: 8 sampler steps through the nodes' own callbacks."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import scripted_ksampler
+    N = ref_shim.load_reference_nodes(scripted_ksampler)
+    R = ref_shim.load_reference()
+    # -- legacy: StableRenderSampler.execute_overlap (legacy_codes/nodes/samplers.py:79-129)
+    CorrespondenceMap = R["correspondence_map"].CorrespondenceMap
+    T, H, W, h, w = 4, 32, 32, 4, 4
+    ids = synthetic.make_ids(T, H, W, tex_h=16, tex_w=16, seed=41, legacy_layout=True, dtype=torch.int16)
+    with tempfile.TemporaryDirectory() as td:
+        iddir = os.path.join(td, "id")
+        os.makedirs(iddir)
+        for f in range(T):
+            np.save(os.path.join(iddir, f"id_{f}.npy"), ids[f].numpy())
+        with ref_shim.quiet():
+            cmap = CorrespondenceMap.FromExisting(iddir, enable_cache=False)
+    torch.manual_seed(3)
+    lat = torch.randn(T, 4, h, w)
+    sched = N["legacy_schedulers"].OverlapScheduler()
+    alpha = sched(start_step=1, interpolate_begin=0.9, interpolate_end=0.3, interpolate_type="linear", power=1.0)
+    radius = sched(interpolate_begin=0.0, interpolate_end=0.0)
+    node = N["legacy_samplers"].StableRenderSampler()
+    out = {}
+    for option, sampler in (("noise", "ddpm"), ("denoised", "ddpm"), ("both", "ddpm"), ("denoised", "ddim")):
+        for algo in ("average", "frame_distance"):
+            with ref_shim.quiet():
+                res = node(None, None, None, {"samples": lat.clone()}, cmap, alpha, radius, overlap_algorithm=algo,
+                           apply_overlap_option=option, steps=8, sampler_name=sampler)
+            out[f"legacy_{option}_{sampler}_{algo}"] = res[0]["samples"].numpy()
+    # -- current generation: CorrespondSampler + the OverlapCorresponder node (_nodes/samplers.py:71-201)
+    F, Hc, hc = 4, 64, 8
+    ids_c = synthetic.make_ids(F, Hc, Hc, tex_h=32, tex_w=32, frac_2048=0.05, seed=43)
+    x = torch.randn(F, 4, hc, hc)
+    ed = _EngineData(R["corrmap"].IDMap(tensor=ids_c.clone()))
+    ed.noise_maps = x.clone()
+    with ref_shim.quiet():
+        corresponder, vae_cb = N["samplers"].OverlapCorresponder()(ed, step_finished_inject_ratio=0.5)
+        res = N["samplers"].CorrespondSampler()(None, None, None, corresponder, ed, steps=8, sampler_name="ddpm")
+    out["current_overlap_ddpm"] = res["samples"].numpy()
+    save("node_samplers", legacy_ids=ids.numpy(), legacy_latents=lat.numpy(), ids=ids_c.numpy(), latents=x.numpy(), **out)
+
+
 def main():
     if "--only-ingest" in sys.argv:
         torch.set_num_threads(1)
@@ -427,6 +471,10 @@ def main():
     if "--only-latent-init" in sys.argv:
         torch.set_num_threads(1)
         latent_init_cases(ref_shim.load_reference())
+        return
+    if "--only-nodes" in sys.argv:
+        torch.set_num_threads(1)
+        node_cases()
         return
     if not ref_shim.available():
         raise SystemExit("reference tree not mounted; fixtures can only be regenerated in the build container")
@@ -440,6 +488,7 @@ def main():
     legacy_cases(R)
     latent_init_cases(R)
     ingest_cases(R)
+    node_cases()
 
 
 if __name__ == "__main__":

@@ -251,3 +251,53 @@ def quiet():
     """Silences the reference's stray print() calls (corrmap.py:276,722; corresponder.py:345-347)."""
     with contextlib.redirect_stdout(io.StringIO()):
         yield
+
+
+def _extract_function(relpath: str, name: str, namespace: dict):
+    """Executes ONE top-level function of a reference file, unmodified, without importing the file (whose other
+    imports — typeguard, pydantic — are absent here)."""
+    import ast
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    with open(path) as f:
+        src = f.read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
+            exec(code, namespace)
+            return namespace[name]
+    raise KeyError(name)
+
+
+def load_reference_nodes(ksampler) -> dict:
+    """The reference's node files (legacy_codes/nodes/{samplers,schedulers}.py and
+    source/comfyUI/stable_rendering/_nodes/samplers.py), unmodified, wired to `ksampler` in place of ComfyUI's
+    `custom_ksampler` (the sampler belongs to the host application; a scripted one drives the callbacks in fixtures)."""
+    import inspect
+    import re
+    from typing import Any, Optional
+    R = load_reference()
+
+    class _Choices:
+        __args__ = ("euler", "ddim", "ddpm")
+
+    ct = sys.modules["comfyUI.types"]
+    ct.__dict__.update(
+        StableRenderingNode=type("StableRenderingNode", (), {}), INT=lambda *a, **k: int, FLOAT=lambda *a, **k: float,
+        LATENT=dict, MODEL=Any, EngineData=Any, SamplingCallbackContext=Any, VAEDecodeCallback=Any,
+        COMFY_SAMPLERS=_Choices, COMFY_SCHEDULERS=_Choices, UIImage=lambda *a, **k: None, Optional=Optional)
+    _stub("comfyUI.nodes", custom_ksampler=ksampler)
+    _stub("common_utils.type_utils",
+          is_empty_method=_extract_function("source/common_utils/type_utils.py", "is_empty_method",
+                                            {"inspect": inspect, "re": re}))
+    sru = sys.modules["common_utils.stable_render_utils"]
+    sru.Corresponder = R["corresponder"].Corresponder
+    sru.DefaultCorresponder = R["corresponder"].DefaultCorresponder
+    sru.OverlapCorresponder = R["corresponder"].OverlapCorresponder
+    _stub("stable_rendering.src.overlap", ResizeOverlap=R["overlap"].ResizeOverlap, Scheduler=R["overlap_scheduler"].Scheduler,
+          overlap_algorithm_factory=R["algorithms"].overlap_algorithm_factory)
+    _stub("stable_rendering.src.overlap.overlap_scheduler", Scheduler=R["overlap_scheduler"].Scheduler)
+    out = {}
+    out["legacy_samplers"] = _load("legacy_nodes.samplers", "legacy_codes/nodes/samplers.py")
+    out["legacy_schedulers"] = _load("legacy_nodes.schedulers", "legacy_codes/nodes/schedulers.py")
+    out["samplers"] = _load("ref_nodes.samplers", "source/comfyUI/stable_rendering/_nodes/samplers.py")
+    return out

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libsrx.so")
 
 # ---- enums (include/srx.h) ---------------------------------------------------------------------------------
 SRX_OK, SRX_ERR_INVALID, SRX_ERR_INDEX, SRX_ERR_CUDA, SRX_ERR_UNSUPPORTED, SRX_ERR_KEY_RANGE = 0, -1, -2, -3, -4, -5
+SRX_ERR_PEER_LOST = -6
 SRX_F32, SRX_F16, SRX_BF16, SRX_I32, SRX_I16, SRX_U8 = 0, 1, 2, 10, 11, 20
 SRX_KEY_VERTEX, SRX_KEY_TUPLE = 0, 1
 SRX_STRATEGY = {"average": 0, "frame_distance": 1, "pixel_distance": 2, "perpendicular_view_normal": 3}
@@ -86,6 +87,11 @@ class srx_ingest_args(C.Structure):
                 ("noise_maps", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
+class srx_gbuffer_arrays(C.Structure):
+    _fields_ = [("color", C.c_void_p), ("ids", C.c_void_p), ("pos", C.c_void_p), ("normal_depth", C.c_void_p),
+                ("noise", C.c_void_p), ("canny", C.c_void_p), ("canny_dtype", C.c_int)]
+
+
 class srx_gbuffer_temp(C.Structure):
     _fields_ = [("color", C.c_void_p), ("ids", C.c_void_p), ("pos", C.c_void_p), ("normal", C.c_void_p), ("depth", C.c_void_p),
                 ("noise", C.c_void_p), ("canny", C.c_void_p)]
@@ -147,10 +153,18 @@ _PROTOTYPES = {
     "srx_tensor_to_array": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p]),
     "srx_array_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "srx_array_to_tensor_ch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "srx_tensor_to_array_ch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_uint, C.c_void_p]),
+    "srx_atlas_to_array": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "srx_gl_mapped_layer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "srx_array_free": (C.c_int, [C.c_void_p]),
     "srx_ingest_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "srx_frame_ingest": (C.c_int, [C.POINTER(srx_ingest_args), C.c_void_p]),
     "srx_gbuffer_merge_closer": (C.c_int, [C.POINTER(srx_gbuffer), C.c_int, C.c_int, C.c_int, C.POINTER(srx_gbuffer_temp), C.c_void_p]),
+    "srx_frame_ingest_arrays": (C.c_int, [C.POINTER(srx_ingest_args), C.POINTER(srx_gbuffer_arrays), C.c_void_p]),
+    "srx_gbuffer_merge_closer_arrays": (C.c_int, [C.POINTER(srx_gbuffer_arrays), C.c_int, C.c_int, C.c_int,
+                                                  C.POINTER(srx_gbuffer_temp), C.c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -124,7 +124,8 @@ class OverlapCorresponder:
 
     # -- the hot path ----------------------------------------------------------------------------------------------
     def _plan(self, engine_data, id_map: IDMap, x: torch.Tensor) -> OverlapPlan:
-        key = (x.device, tuple(x.shape), self.deterministic)
+        key = (x.device, tuple(x.shape), self.deterministic, int(self.key_capacity), self.exchange,
+               self.process_group is not None)
         plan = id_map._plans.get(key)
         if plan is None:
             cap = int(self.key_capacity)

@@ -164,11 +164,20 @@ class IDMap:
         (corrmap.py:226,278) and avoids it by building a new IDMap per batch; this keeps plans (and, frame-sharded, their
         symmetric-memory workspaces) alive across batches."""
         self._vertex_screen_info_cache = None
-        for plan in self._plans.values():
-            plan.cached = False
-            plan._calls = 0
         same = self._device_ids.get(self.tensor.device) if isinstance(self.tensor, Tensor) else None
         self._device_ids = {self.tensor.device: same} if same is not None and same.data_ptr() == self.tensor.data_ptr() else {}
+        for key, plan in list(self._plans.items()):
+            plan.cached = False
+            plan._calls = 0
+            plan._checked = False          # a capacity hint must be re-validated against the new ids (first step checks)
+            # the plan streams `plan._ids`: point it at the NEW content.  When the device copy aliases `tensor` it already
+            # is; otherwise (CPU tensor, int64 ids, another device) a fresh device copy is made here.
+            fresh = self.device_ids(plan.device)
+            if tuple(fresh.shape) != tuple(plan.id_shape) or fresh.dtype != plan.id_dtype:
+                plan.close()
+                del self._plans[key]
+            else:
+                plan._ids = fresh
 
     def create_vertex_screen_info(self) -> Tensor:
         """[N,7] float32 (object, material, map_index, vertex_id, x/H, y/W, frame_index) in (frame,y,x) order —
@@ -477,6 +486,37 @@ class CorrespondMap:
             _lib.check(_lib.load().srx_atlas_dequantize(vq.data_ptr(), fq.data_ptr(), m._values.data_ptr(), m._writtens.data_ptr(),
                                                         vq.numel(), fq.numel(), _lib.current_stream_ptr(m.device)))
         return m
+
+    # -- atlas -> GL_TEXTURE_2D_ARRAY (reference CorrespondMap.load / set_data, corrmap.py:443-489) --------------------
+    def load(self, texture=None, arrays=None, transpose: bool = True):
+        """Uploads the k*k atlas layers into the `GL_TEXTURE_2D_ARRAY` the G-buffer shader samples
+        (default_Gbuffer.frag.glsl:186-200) without leaving the GPU.  The reference round-trips every layer through the host
+        (`get_map(i, order='whc').cpu().numpy()` -> `glTexSubImage3D`, corrmap.py:470-480); here one kernel per layer writes
+        the layer's mapped cudaArray from the fp16 atlas, with the reference's 'whc' transpose (texel (x, y) =
+        `_values[i, x * width + y]`) done through a shared-memory tile.
+
+        texture: a `stable_renderer_b200.texture.Texture` wrapping the engine's GL_TEXTURE_2D_ARRAY (RGBA16F / RG16F / R16F
+                 with k*k layers; RGB16F cannot be registered with CUDA, renderManager.py:268), or
+        arrays:  a list of k*k `cudaArray_t` handles (one per layer) — tests and headless tools."""
+        k2 = self.k * self.k
+        if self.channel_count not in (1, 2, 4):
+            raise NotImplementedError("CUDA arrays hold 1, 2 or 4 channels: a 3-channel atlas (RGB16F) has no CUDA mapping")
+        lib = _lib.load()
+        if (texture is None) == (arrays is None):
+            raise ValueError("pass either the Texture of the GL array texture or the list of per-layer cudaArray handles")
+        if arrays is not None and len(arrays) != k2:
+            raise ValueError(f"{k2} layer arrays expected, got {len(arrays)}")
+        layer_bytes = self.height * self.width * self.channel_count * 2
+        try:
+            for i in range(k2):
+                arr = texture.map_array(layer=i) if texture is not None else int(arrays[i])
+                with torch.cuda.device(self.device):
+                    _lib.check(lib.srx_atlas_to_array(arr, self._values.data_ptr() + i * layer_bytes, self.height, self.width,
+                                                      self.channel_count, 1 if transpose else 0, _lib.current_stream_ptr(self.device)))
+        finally:
+            if texture is not None:
+                for _ in range(k2):
+                    texture.unmap_array()
 
     def load_vertex_screen_info(self, id_map: IDMap):
         self.vertex_screen_info = id_map.create_vertex_screen_info()

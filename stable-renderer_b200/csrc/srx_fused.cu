@@ -36,7 +36,9 @@
 #define FZ_SLOT_BITS 25
 #define FZ_BU 4                           // cells per thread per round of the gather phase
 
-enum { FZ_ST_KEY_RANGE = 0 };
+enum { FZ_ST_KEY_RANGE = 0, FZ_ST_TIMEOUT = 2 };   // status words (srx_plan_check); 1 = ST_CELL_RANGE of the split kernels
+#define FZ_SPIN_FAST 8192u                // polls before a waiter starts backing off
+#define FZ_SPIN_LIMIT (1u << 21)          // backed-off polls (~1 us each) before a wait gives up: ~2 s
 // What the kernel does with the ids:
 //   STEP    the streaming overlap step (ids new for this call)
 //   MARK    bucketing pass 1 — phase A only: winners, the byte map of winner keys, pairs per CTA.  No reductions.
@@ -88,7 +90,8 @@ struct FzParams {
     int2 *pool;               // cached plan: (slot, cell << 6 | multiplicity - 1) entries, one region per CTA
     float *cnt_plan;          // cached plan: [kcap] entries per key on this rank (filled by EMIT; counts depend on the ids only)
     int dbg;                  // SRX_FZ_DEBUG experiment bits (results are wrong when set): 1 = no reductions,
-                              // 2 = consumers only drain the ring, 4 = stop after phase A
+                              // 2 = consumers only drain the ring, 4 = stop after phase A, 8 = no count reductions,
+                              // 16 = no sum reductions
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -210,13 +213,53 @@ __device__ __forceinline__ FzRec fz_rec_load(const char *p) {
     r.flag = f;
     return r;
 }
-__device__ __forceinline__ FzRec fz_rec_wait(const char *p, unsigned flag) {
+__device__ __forceinline__ FzRec fz_rec_wait(const char *p, unsigned flag, int *status) {
     FzRec r = fz_rec_load(p);
+    unsigned spins = 0;
     while (r.flag != flag) {
         __nanosleep(200);   // thousands of threads wait at once: back off instead of saturating L2 with polls
+        if (++spins > FZ_SPIN_LIMIT || *reinterpret_cast<volatile int *>(status + FZ_ST_TIMEOUT)) {
+            atomicOr(status + FZ_ST_TIMEOUT, 1);
+            break;
+        }
         r = fz_rec_load(p);
     }
     return r;
+}
+
+// 32-byte statistics record {3 doubles, step}: the 16 AdaIN partial sums of one CTA travel as six of them, each written
+// with ONE 256-bit store and polled with ONE 256-bit load, so a reader that sees this step's number also sees the data.
+// No atomics, no fence, no arrival counter; records never need clearing (step numbers only grow).
+__device__ __forceinline__ void fz_stat_store(char *p, double a, double b, double c, unsigned flag) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(__double2loint(a)), "r"(__double2hiint(a)), "r"(__double2loint(b)), "r"(__double2hiint(b)),
+                   "r"(__double2loint(c)), "r"(__double2hiint(c)), "r"(flag), "r"(0u) : "memory");
+}
+__device__ __forceinline__ unsigned fz_stat_load(const char *p, double &a, double &b, double &c) {
+    unsigned r0, r1, r2, r3, r4, r5, f, z;
+    asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(f), "=r"(z) : "l"(p) : "memory");
+    a = __hiloint2double((int)r1, (int)r0);
+    b = __hiloint2double((int)r3, (int)r2);
+    c = __hiloint2double((int)r5, (int)r4);
+    return f;
+}
+
+// Bounded spin: wait until *p has reached `target` (monotonic counter).  A peer that died, skipped a step or launched a
+// different grid would otherwise hang every GPU of the box inside a cooperative kernel: after ~2 s the waiter sets the
+// TIMEOUT status word (srx_plan_check reports it) and carries on, and every later wait of this launch gives up at once.
+__device__ __forceinline__ bool fz_wait_ge(const unsigned *p, unsigned target, bool sys, int *status) {
+    unsigned spins = 0;
+    while ((int)(ld_relaxed(p, sys) - target) < 0) {
+        if (++spins > FZ_SPIN_FAST) {
+            __nanosleep(500);
+            if (spins > FZ_SPIN_FAST + FZ_SPIN_LIMIT || *reinterpret_cast<volatile int *>(status + FZ_ST_TIMEOUT)) {
+                atomicOr(status + FZ_ST_TIMEOUT, 1);
+                return false;
+            }
+        }
+    }
+    return true;
 }
 
 // Grid-wide (and, with peers, box-wide) barrier `b`: every CTA adds 1 to counter [b][my rank] on each participant and
@@ -235,38 +278,37 @@ __device__ __forceinline__ void fz_barrier(const FzParams &P, int b, unsigned ta
         else red_release_add(pad, 1u, false);
         const int src = cross ? (int)threadIdx.x : P.rank;
         const unsigned *mine = reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + b * SRX_MAX_PEERS + src;
-        while ((int)(ld_relaxed(mine, sys) - target) < 0) { }
+        fz_wait_ge(mine, target, sys, P.status);
         // no acquire fence: everything read after this barrier that another SM (or GPU) wrote is loaded past L1
         // (ld.cg / ld.relaxed.sys); the fence would only add an L1 invalidation and ~0.7 us
     }
     __syncthreads();
 }
 
-// key of one pixel: the dense slot of float32(vertexID) (corresponder.py:331-334, corrmap.py:256-261) or -1 when the
-// pixel is no entry (map_index == 2048 or an all-zero id, corrmap.py:266-275)
+// the dense slot of float32(vertexID) (corresponder.py:331-334, corrmap.py:256-261)
 // float32(v) in integer arithmetic: exact below 2^24; in [2^24, 2^25) floats are 2 apart and ties go to the even
 // mantissa, i.e. the multiple of 4; from 2^25 on the value is past any slot table (capacity <= 2^25) whatever it rounds to.
 __device__ __forceinline__ int fz_slot_of(int v) {
     return ((unsigned)v >> 24) == 1u ? ((v + ((v >> 1) & 1)) & ~1) : v;
 }
-__device__ __forceinline__ int fz_key(int s, int m, int i, int v, unsigned kcap, int *status) {
+// Raw key of one pixel: its vertex id (float32-rounded when the table is large enough for that to matter) when the pixel
+// is an entry — map_index != 2048 and not an all-zero id, corrmap.py:266-275 — else -1.  The range check against the slot
+// table happens once per cell, on the warp-wide maximum.  (A vertex id of exactly -1 is therefore read as "no id".)
+__device__ __forceinline__ int fz_key_raw(int s, int m, int i, int v, bool big) {
     const bool valid = (i != SRX_NO_ID_MAP_INDEX) & ((s | m | i | v) != 0);
-    const int slot = fz_slot_of(v);
-    const bool inr = (unsigned)slot < kcap;
-    if (valid & !inr) atomicOr(status + FZ_ST_KEY_RANGE, 1);
-    return (valid & inr) ? slot : -1;
+    if (big) v = fz_slot_of(v);
+    return valid ? v : -1;
 }
-
-template <typename IdT> __device__ __forceinline__ void fz_keys(uint32_t a, unsigned kcap, int *status, int &ka, int &kb);
-template <> __device__ __forceinline__ void fz_keys<int4>(uint32_t a, unsigned kcap, int *status, int &ka, int &kb) {
+template <typename IdT> __device__ __forceinline__ void fz_keys_raw(uint32_t a, bool big, int &ka, int &kb);
+template <> __device__ __forceinline__ void fz_keys_raw<int4>(uint32_t a, bool big, int &ka, int &kb) {
     const int4 A = lds128(a), B = lds128(a + 16);
-    ka = fz_key(A.x, A.y, A.z, A.w, kcap, status);
-    kb = fz_key(B.x, B.y, B.z, B.w, kcap, status);
+    ka = fz_key_raw(A.x, A.y, A.z, A.w, big);
+    kb = fz_key_raw(B.x, B.y, B.z, B.w, big);
 }
-template <> __device__ __forceinline__ void fz_keys<short4>(uint32_t a, unsigned kcap, int *status, int &ka, int &kb) {
+template <> __device__ __forceinline__ void fz_keys_raw<short4>(uint32_t a, bool big, int &ka, int &kb) {
     const int4 v = lds128(a);
-    ka = fz_key((int)(short)(v.x & 0xffff), v.x >> 16, (int)(short)(v.y & 0xffff), v.y >> 16, kcap, status);
-    kb = fz_key((int)(short)(v.z & 0xffff), v.z >> 16, (int)(short)(v.w & 0xffff), v.w >> 16, kcap, status);
+    ka = fz_key_raw((int)(short)(v.x & 0xffff), v.x >> 16, (int)(short)(v.y & 0xffff), v.y >> 16, big);
+    kb = fz_key_raw((int)(short)(v.z & 0xffff), v.z >> 16, (int)(short)(v.w & 0xffff), v.w >> 16, big);
 }
 
 __device__ __forceinline__ double fz_warp_sum(double v) {
@@ -420,16 +462,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             float4 *other = reinterpret_cast<float4 *>(P.ws + (long long)(par ^ 1) * P.accum_stride);
             if (P.world > 1) {
                 const unsigned done = (epoch - 1u) * gridDim.x;
-                for (int q = 0; q < P.world; ++q) {
-                    const unsigned *c = reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + 1 * SRX_MAX_PEERS + q;
-                    while ((int)(ld_relaxed(c, true) - done) < 0) { }
-                }
+                for (int q = 0; q < P.world; ++q)
+                    fz_wait_ge(reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + 1 * SRX_MAX_PEERS + q, done, true, P.status);
             }
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             const int stride = gridDim.x * FZ_CONS * 32;
             for (int v = blockIdx.x * FZ_CONS * 32 + tid; v < P.accum_vec; v += stride) other[v] = z;
-            float4 *st_other = reinterpret_cast<float4 *>(P.ws + P.stats_off + (long long)(par ^ 1) * P.batch * 128);
-            for (int v = blockIdx.x * FZ_CONS * 32 + tid; v < P.batch * 8; v += stride) st_other[v] = z;
         }
         // the counts depend on the ids only: copy them from the plan instead of reducing them again (the count region
         // of this step's accumulator was cleared during the previous step and nothing else writes it in this mode)
@@ -512,7 +550,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             const uint32_t full = sbase + L::BAR_OFF + stage * 8;
             if (item >= nitems) {                    // end marker for the consumers
                 if (lane == 0) {
-                    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sb + L::DESC_OFF), "r"(0), "r"(-1) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb + L::DESC_OFF), "r"(0), "r"(-1), "r"(0), "r"(0) : "memory");
                     mbar_arrive(full);
                 }
                 break;
@@ -525,17 +563,18 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             const int sx0 = chunk * FZ_CELLS;
             const int ncell = min(FZ_CELLS, P.w - sx0);
             if (lane == 0) {
-                asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sb + L::DESC_OFF), "r"((fl * P.h + sy) * P.w + sx0), "r"(ncell) : "memory");
-                mbar_expect_tx(full, (uint32_t)(ncell * (64 * FzId<IdT>::PX + (with_x ? 4 * (int)sizeof(XT) : 0))));
+                // descriptor: first cell of the stage in the winner array, cells in the stage, element offset of the
+                // cells' channel-0 latents.  The latents themselves are fetched by the consumers with plain loads (eight
+                // scalars per warp): four more tiny bulk copies per stage cost 10 % of the streaming rate
+                // (tools/streamprobe, profiles/r2_streamprobe.txt)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb + L::DESC_OFF), "r"((fl * P.h + sy) * P.w + sx0), "r"(ncell),
+                             "r"((fl * 4 * P.h + sy) * P.w + sx0), "r"(0) : "memory");
+                mbar_expect_tx(full, (uint32_t)(ncell * 64 * FzId<IdT>::PX));
             }
             __syncwarp();
             if (lane < 8) {
                 const long long px = ((long long)g * P.H + sy * 8 + lane) * P.W + sx0 * 8;
                 bulk_g2s_hint(sb + lane * FzId<IdT>::PITCH, ids + px * FzId<IdT>::PX, (uint32_t)(ncell * 8 * FzId<IdT>::PX), full, pol);
-            } else if (lane < 12 && with_x) {
-                const int ch = lane - 8;
-                bulk_g2s(sb + L::LAT_OFF + ch * FZ_CELLS * (int)sizeof(XT),
-                         x + ((long long)(fl * 4 + ch) * P.h + sy) * P.w + sx0, (uint32_t)(ncell * (int)sizeof(XT)), full);
             }
             if (++stage == FZ_STAGES) { stage = 0; ph ^= 1u; }
         }
@@ -544,96 +583,138 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         if (P.mode == FZ_MODE_STEP) {
             if (P.world > 1) {   // peers pulled from that accumulator during the previous step: wait until all are done
                 const unsigned done = (epoch - 1u) * gridDim.x;
-                for (int q = 0; q < P.world; ++q) {
-                    const unsigned *c = reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + 1 * SRX_MAX_PEERS + q;
-                    while ((int)(ld_relaxed(c, true) - done) < 0) { }
-                }
+                for (int q = 0; q < P.world; ++q)
+                    fz_wait_ge(reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + 1 * SRX_MAX_PEERS + q, done, true, P.status);
             }
             float4 *other = reinterpret_cast<float4 *>(P.ws + (long long)(par ^ 1) * P.accum_stride);
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             const int stride = gridDim.x * FZ_CONS * 32;
             for (int v = blockIdx.x * FZ_CONS * 32 + tid; v < P.accum_vec; v += stride) other[v] = z;
-            float4 *st_other = reinterpret_cast<float4 *>(P.ws + P.stats_off + (long long)(par ^ 1) * P.batch * 128);
-            for (int v = blockIdx.x * FZ_CONS * 32 + tid; v < P.batch * 8; v += stride) st_other[v] = z;
         }
         const int r = lane >> 2, pr = lane & 3;
         const uint32_t lane_off = r * FzId<IdT>::PITCH + pr * 2 * FzId<IdT>::PX;
+        const bool big = P.kcap > (1u << 24);     // only then can a vertex id lose bits on its way through float32
+        const XT *xg = reinterpret_cast<const XT *>(P.x);
+        const int c0 = warp * FZ_CPW;             // this warp's first cell in every stage
+        const unsigned SLOT_MASK = (1u << FZ_SLOT_BITS) - 1u;
+        int bad = 0;
         int stage = 0;
         unsigned ph = 0;
         while (true) {
             mbar_wait(sbase + L::BAR_OFF + stage * 8, ph);
             const uint32_t sb = sbase + stage * L::STAGE;
-            const int2 desc = lds64(sb + L::DESC_OFF);
+            const int4 desc = lds128(sb + L::DESC_OFF);
             if (desc.y < 0) break;                    // end marker
+            // this warp's latents (FZ_CPW cells x 4 channels, lanes 0..7): requested now, used after the key work
+            float xl = 0.f;
+            if (with_x && lane < 4 * FZ_CPW && c0 + (lane >> 2) < desc.y)
+                xl = XIo<XT>::ld(xg + desc.z + (long long)(lane & 3) * n + c0 + (lane >> 2));
             int ka[FZ_CPW], kb[FZ_CPW];
-            float xv[FZ_CPW][4];
 #pragma unroll
             for (int u = 0; u < FZ_CPW; ++u) {
-                const int cell = warp * FZ_CPW + u;
-                ka[u] = kb[u] = -1;
-                if (cell < desc.y)   // warp-uniform (ragged last chunk of a row: the stage holds stale bytes there)
-                    fz_keys<IdT>(sb + lane_off + cell * 8 * FzId<IdT>::PX, P.kcap, P.status, ka[u], kb[u]);
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) xv[u][ch] = lds_x<XT>(sb + L::LAT_OFF + ch * FZ_CELLS * (int)sizeof(XT), cell);
+                fz_keys_raw<IdT>(sb + lane_off + (c0 + u) * 8 * FzId<IdT>::PX, big, ka[u], kb[u]);
+                if (c0 + u >= desc.y) ka[u] = kb[u] = -1;   // warp-uniform (ragged last chunk of a row: stale bytes there)
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(sbase + L::BAR_OFF + (FZ_STAGES + stage) * 8);   // stage may be refilled
             if (++stage == FZ_STAGES) { stage = 0; ph ^= 1u; }
             if (P.dbg & 2) continue;
 
+            // Everything below runs on the warp's FZ_CPW cells side by side, without branches in the common case, so that
+            // the REDUX / shuffle latencies of one cell hide behind the other's (four warps per scheduler cannot hide them).
+            // Keys are raw vertex ids here (-1 = no entry); one warp-wide maximum per cell range-checks all 64 pixels.
+            unsigned um[FZ_CPW];                      // 1 + the cell's largest key, 0 = no entry in the cell
+#pragma unroll
+            for (int u = 0; u < FZ_CPW; ++u) um[u] = __reduce_max_sync(FULL, max((unsigned)ka[u] + 1u, (unsigned)kb[u] + 1u));
+            {
+                unsigned worst = um[0];
+#pragma unroll
+                for (int u = 1; u < FZ_CPW; ++u) worst = max(worst, um[u]);
+                if (worst > P.kcap) {                 // rare: a vertex id outside the slot table — drop those pixels, flag the plan
+                    bad = 1;
+#pragma unroll
+                    for (int u = 0; u < FZ_CPW; ++u) {
+                        if ((unsigned)ka[u] >= P.kcap) ka[u] = -1;
+                        if ((unsigned)kb[u] >= P.kcap) kb[u] = -1;
+                        um[u] = __reduce_max_sync(FULL, max((unsigned)ka[u] + 1u, (unsigned)kb[u] + 1u));
+                    }
+                }
+            }
+            unsigned lo[FZ_CPW], wp[FZ_CPW];
 #pragma unroll
             for (int u = 0; u < FZ_CPW; ++u) {
-                const int cell = warp * FZ_CPW + u;
-                if (cell >= desc.y) break;            // warp-uniform
-                const int a = ka[u], b = kb[u];
-                const int hi = __reduce_max_sync(FULL, max(a, b));
-                if (hi < 0) {                         // no entry in this cell
-                    if (lane == 0) P.winner[desc.x + cell] = -1;
-                    continue;
-                }
+                lo[u] = __reduce_min_sync(FULL, min((unsigned)ka[u], (unsigned)kb[u]));
                 // winner = last valid pixel in row-major order: positions 2*lane (a) and 2*lane+1 (b), stored +1
-                unsigned wp = 0;
-                if (b >= 0) wp = ((unsigned)(2 * lane + 2) << FZ_SLOT_BITS) | (unsigned)b;
-                else if (a >= 0) wp = ((unsigned)(2 * lane + 1) << FZ_SLOT_BITS) | (unsigned)a;
-                wp = __reduce_max_sync(FULL, wp);
-                if (lane == 0) P.winner[desc.x + cell] = (int)(wp & ((1u << FZ_SLOT_BITS) - 1u));
-                const unsigned lo = __reduce_min_sync(FULL, min((unsigned)a, (unsigned)b));
-                if (P.dbg & 1) continue;
-                // reduce-by-key inside the warp -> up to two (key, multiplicity) pairs per lane:
-                //   * one key in the whole cell (REDUX min == max): a single pair for the cell;
-                //   * otherwise the lane's two horizontally adjacent pixels merge when equal, and vertically adjacent rows
-                //     (lane L = row 2i, lane L+4 = row 2i+1, same columns) merge pairwise through two shuffles.  Magnified
-                //     textures (several pixels per texel) are where this pays: every merge saves two L2 atomics.
-                int k1 = a, k2 = (a == b) ? -1 : b, m1 = (a == b) ? 2 : 1, m2 = 1;
-                if ((int)lo == hi) {
-                    const int total = __reduce_add_sync(FULL, (a >= 0) + (b >= 0));
-                    k1 = lane == 0 ? hi : -1;
-                    k2 = -1;
-                    m1 = total;
-                } else {
-                    const bool upper = (lane & 4) == 0;                       // even row of the cell
-                    const int o1 = __shfl_xor_sync(FULL, k1, 4), o2 = __shfl_xor_sync(FULL, k2, 4);
-                    const int om1 = __shfl_xor_sync(FULL, m1, 4);
-                    // first slots: same column pair, rows 2i / 2i+1.  Equal keys: the upper lane takes both.
-                    if (k1 >= 0 && o1 == k1) {
-                        if (upper) m1 += om1; else k1 = -1;
-                    }
-                    if (k2 >= 0 && o2 == k2) {                                // second slots (multiplicity 1 on both sides)
-                        if (upper) m2 += 1; else k2 = -1;
-                    }
+                unsigned w = 0;
+                if (kb[u] >= 0) w = ((unsigned)(2 * lane + 2) << FZ_SLOT_BITS) | (unsigned)kb[u];
+                else if (ka[u] >= 0) w = ((unsigned)(2 * lane + 1) << FZ_SLOT_BITS) | (unsigned)ka[u];
+                wp[u] = __reduce_max_sync(FULL, w);
+            }
+            if (lane < FZ_CPW && c0 + lane < desc.y) {   // lane u stores cell u's winner: one store instruction per stage
+                unsigned w = wp[0], m = um[0];
+#pragma unroll
+                for (int u = 1; u < FZ_CPW; ++u) if (lane == u) { w = wp[u]; m = um[u]; }
+                P.winner[desc.x + c0 + lane] = m ? (int)(w & SLOT_MASK) : -1;
+            }
+            if (P.dbg & 1) continue;
+            {
+                unsigned any = um[0];
+#pragma unroll
+                for (int u = 1; u < FZ_CPW; ++u) any |= um[u];
+                if (any == 0) continue;               // no entry in any of the cells (warp-uniform): outside every object
+            }
+            // reduce-by-key inside the warp -> up to two (key, multiplicity) pairs per lane and cell:
+            //   * the lane's two horizontally adjacent pixels merge when equal, and vertically adjacent rows (lane L = row 2i,
+            //     lane L+4 = row 2i+1, same columns) merge pairwise through shuffles.  Magnified textures (several pixels per
+            //     texel) are where this pays: every merge saves two L2 atomics;
+            //   * one key in the whole cell (min == max): a single pair for the cell.
+            int k1[FZ_CPW], k2[FZ_CPW], m1[FZ_CPW], m2[FZ_CPW];
+            const bool upper = (lane & 4) == 0;       // even row of the cell
+#pragma unroll
+            for (int u = 0; u < FZ_CPW; ++u) {
+                const bool same = ka[u] == kb[u];
+                k1[u] = ka[u];
+                k2[u] = same ? -1 : kb[u];
+                m1[u] = same ? 2 : 1;
+                m2[u] = 1;
+            }
+#pragma unroll
+            for (int u = 0; u < FZ_CPW; ++u) {
+                const int o1 = __shfl_xor_sync(FULL, k1[u], 4), o2 = __shfl_xor_sync(FULL, k2[u], 4);
+                const int om1 = __shfl_xor_sync(FULL, m1[u], 4);
+                // first slots: same column pair, rows 2i / 2i+1.  Equal keys: the upper lane takes both.
+                if (k1[u] >= 0 && o1 == k1[u]) {
+                    if (upper) m1[u] += om1; else k1[u] = -1;
                 }
-                if (P.mode != FZ_MODE_STEP) {
-                    // bucketing passes: the pairs are counted / stored instead of reduced
+                if (k2[u] >= 0 && o2 == k2[u]) {      // second slots (multiplicity 1 on both sides)
+                    if (upper) m2[u] += 1; else k2[u] = -1;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < FZ_CPW; ++u) {
+                if (um[u] != 0 && lo[u] + 1u == um[u]) {          // warp-uniform: one key in the whole cell
+                    const int total = __reduce_add_sync(FULL, (ka[u] >= 0) + (kb[u] >= 0));
+                    k1[u] = lane == 0 ? (int)lo[u] : -1;
+                    k2[u] = -1;
+                    m1[u] = total;
+                }
+            }
+            if (P.mode != FZ_MODE_STEP) {
+                // bucketing passes: the pairs are counted / stored instead of reduced
+#pragma unroll
+                for (int u = 0; u < FZ_CPW; ++u) {
+                    if (um[u] == 0) continue;         // warp-uniform
+                    const int cell = c0 + u;
                     if (P.mode == FZ_MODE_MARK) {
-                        const int w = (int)(wp & ((1u << FZ_SLOT_BITS) - 1u));
-                        const int np = __popc(__ballot_sync(FULL, k1 >= 0)) + __popc(__ballot_sync(FULL, k2 >= 0));
+                        const int w = (int)(wp[u] & SLOT_MASK);
+                        const int np = __popc(__ballot_sync(FULL, k1[u] >= 0)) + __popc(__ballot_sync(FULL, k2[u] >= 0));
                         if (lane == 0) {
                             P.need[w] = 1;
                             atomicAdd(s_fill, (unsigned)np);
                         }
                     } else {   // EMIT
-                        const bool fa = k1 >= 0 && __ldg(P.need + k1) != 0;
-                        const bool fb = k2 >= 0 && __ldg(P.need + k2) != 0;
+                        const bool fa = k1[u] >= 0 && __ldg(P.need + k1[u]) != 0;
+                        const bool fb = k2[u] >= 0 && __ldg(P.need + k2[u]) != 0;
                         const unsigned ba = __ballot_sync(FULL, fa), bb = __ballot_sync(FULL, fb);
                         const int tot = __popc(ba) + __popc(bb);
                         unsigned base = 0;
@@ -643,28 +724,34 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
                         const unsigned cellg = (unsigned)(desc.x + cell) << 6;
                         int2 *dst = P.pool + P.cta_tab[2 * gridDim.x + blockIdx.x] + base;
                         if (fa) {
-                            dst[__popc(ba & lt)] = make_int2(k1, (int)(cellg | (unsigned)(m1 - 1)));
-                            red_add_f32(P.cnt_plan + k1, (float)m1);
+                            dst[__popc(ba & lt)] = make_int2(k1[u], (int)(cellg | (unsigned)(m1[u] - 1)));
+                            red_add_f32(P.cnt_plan + k1[u], (float)m1[u]);
                         }
                         if (fb) {
-                            dst[__popc(ba) + __popc(bb & lt)] = make_int2(k2, (int)(cellg | (unsigned)(m2 - 1)));
-                            red_add_f32(P.cnt_plan + k2, (float)m2);
+                            dst[__popc(ba) + __popc(bb & lt)] = make_int2(k2[u], (int)(cellg | (unsigned)(m2[u] - 1)));
+                            red_add_f32(P.cnt_plan + k2[u], (float)m2[u]);
                         }
                     }
-                    continue;
                 }
-                if (k1 >= 0) {
-                    const float fm = (float)m1;
-                    red_add_f32x4(acc + (long long)k1 * 4, fm * xv[u][0], fm * xv[u][1], fm * xv[u][2], fm * xv[u][3]);
-                    red_add_f32(cnt + k1, fm);
+                continue;
+            }
+#pragma unroll
+            for (int u = 0; u < FZ_CPW; ++u) {
+                const float x0 = __shfl_sync(FULL, xl, 4 * u), x1 = __shfl_sync(FULL, xl, 4 * u + 1),
+                            x2 = __shfl_sync(FULL, xl, 4 * u + 2), x3 = __shfl_sync(FULL, xl, 4 * u + 3);
+                if (k1[u] >= 0) {
+                    const float fm = (float)m1[u];
+                    if (!(P.dbg & 16)) red_add_f32x4(acc + (long long)k1[u] * 4, fm * x0, fm * x1, fm * x2, fm * x3);
+                    if (!(P.dbg & 8)) red_add_f32(cnt + k1[u], fm);
                 }
-                if (k2 >= 0) {
-                    const float fm = (float)m2;
-                    red_add_f32x4(acc + (long long)k2 * 4, fm * xv[u][0], fm * xv[u][1], fm * xv[u][2], fm * xv[u][3]);
-                    red_add_f32(cnt + k2, fm);
+                if (k2[u] >= 0) {
+                    const float fm = (float)m2[u];
+                    if (!(P.dbg & 16)) red_add_f32x4(acc + (long long)k2[u] * 4, fm * x0, fm * x1, fm * x2, fm * x3);
+                    if (!(P.dbg & 8)) red_add_f32(cnt + k2[u], fm);
                 }
             }
         }
+        if (bad) atomicOr(P.status + FZ_ST_KEY_RANGE, 1);
     }
 
     if (P.mode == FZ_MODE_MARK || P.mode == FZ_MODE_EMIT) {   // bucketing passes end here; the step counter does not move
@@ -715,8 +802,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         // ... and wait until every rank's records are complete: polling a record over NVLink before it is written costs
         // a round trip per retry, polling these local counters costs nothing
         if (tid < P.world) {
-            const unsigned *c = reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + 1 * SRX_MAX_PEERS + tid;
-            while ((int)(ld_relaxed(c, true) - target) < 0) { }
+            fz_wait_ge(reinterpret_cast<const unsigned *>(P.ws + P.pads_off) + 1 * SRX_MAX_PEERS + tid, target, true, P.status);
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
         __syncthreads();
@@ -724,42 +810,66 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
     }
 
     // ------------------------------------------------------------------------------------------------- phases B, C
-    // Each latent frame is handled by a group of `grp` CTAs (grp = gridDim / frames when there are fewer frames than
-    // CTAs — measured: 1024 cells per CTA beat 4096 by 4 us on cfg2 — else 1 and a CTA walks over several frames).
-    // Only the CTAs of one frame exchange statistics, through that frame's own arrival counter, so no grid-wide barrier
-    // separates gather and AdaIN.  The latents read for the gather stay in shared memory (the ring is idle by now) for
-    // the AdaIN pass.
+    // All cells of all latent frames form one linear range that is cut into gridDim equal pieces: CTA c owns the cells
+    // [start(c), start(c+1)), i.e. one or more SEGMENTS (frame f, cells [a, b) of it).  Equal pieces keep every SM busy
+    // whatever the frame count (96 frames on 148 SMs used to leave 52 SMs idle and the others with a whole 16 K-cell
+    // frame each: 39 us of gather + AdaIN on cfg3).
+    //   B  per segment: winner's mean, blend, the 16 partial sums (x, x^2, b, b^2 per channel), block-reduced and
+    //      published as six flagged 32-byte records in slot (c + f) — unique, since c and f only grow along the range.
+    //   C  per segment: poll the records of every CTA that owns a piece of frame f (one L2 round trip once they have
+    //      landed; nobody waits inside phase B, so the polls cannot deadlock), fold them in CTA order — every CTA of a
+    //      frame computes bit-identical statistics — and re-standardise the own cells.
+    // The latents read in B stay in shared memory (the ring is idle by now) for C.
     XT *x = reinterpret_cast<XT *>(P.x);
     double *red = reinterpret_cast<double *>(smem + L::RED_OFF);
     float *coef = reinterpret_cast<float *>(smem + L::COEF_OFF);
-    double *stats = reinterpret_cast<double *>(P.ws + P.stats_off) + (long long)par * P.batch * 16;
-    unsigned *fcount = reinterpret_cast<unsigned *>(P.ws + P.stats_off + (long long)2 * P.batch * 128);
     const int G = gridDim.x;
-    const int grp = P.batch >= G ? 1 : G / P.batch;
-    float4 *sx4 = reinterpret_cast<float4 *>(smem);                       // [cells of this CTA] staged latents
-    const int smem_cells = (int)(FZ_STAGES * L::STAGE / 16);
-    const int f_first = grp == 1 ? (int)blockIdx.x : (int)blockIdx.x / grp;
-    const int f_step = grp == 1 ? G : P.batch;          // grouped CTAs handle exactly one frame
-    const int part = grp == 1 ? 0 : (int)blockIdx.x % grp;
-    for (int f = f_first; f < P.batch; f += f_step) {
-        const int s0 = (int)((long long)n * part / grp), s1 = (int)((long long)n * (part + 1) / grp);
+    float4 *sx4 = reinterpret_cast<float4 *>(smem);                       // staged latents of this CTA's cells
+    const long long smem_cells = (long long)(FZ_STAGES * L::STAGE / 16);
+    const long long NC = (long long)P.batch * n;
+    // Two ways of cutting the range.  ALIGNED (at least two CTAs per frame): every frame is cut into grp = G / batch equal
+    // pieces, one per CTA — one segment, one block reduction and one record poll per CTA, which is what matters when the
+    // whole phase takes a few microseconds.  LINEAR (otherwise): gridDim equal pieces regardless of frame boundaries.
+    const int grp = 2 * P.batch <= G ? G / P.batch : 0;
+    auto cta_start = [&](int c) -> long long {
+        if (grp) {
+            if (c >= P.batch * grp) return NC;
+            const int f = c / grp, part = c - f * grp;
+            return (long long)f * n + (((long long)n * part / grp) & ~7ll);
+        }
+        return c >= G ? NC : ((NC * c) / G) & ~7ll;
+    };
+    const long long beg = cta_start((int)blockIdx.x), end = cta_start((int)blockIdx.x + 1);
+    char *slots = P.ws + P.stats_off;
+    for (long long p0 = beg; p0 < end;) {
+        const int f = (int)(p0 / n);
+        const int s0 = (int)(p0 - (long long)f * n);
+        const int s1 = (int)min((long long)n, end - (long long)f * n);
+        const long long soff = p0 - beg - s0;                             // staged index of cell ci of this segment = soff + ci
+        p0 += s1 - s0;
         XT *xf = x + (long long)f * 4 * n;
         const int *wf = P.winner + (long long)f * n;
-        const bool staged = (s1 - s0) <= smem_cells;
         double sums[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) sums[j] = 0.0;
+        int slot_next[FZ_BU];
+#pragma unroll
+        for (int u = 0; u < FZ_BU; ++u) {
+            const int ci = s0 + tid + u * FZ_THREADS;
+            slot_next[u] = ci < s1 ? __ldcg(wf + ci) : -2;
+        }
         for (int c0 = s0 + tid; c0 < s1; c0 += FZ_BU * FZ_THREADS) {
-            // FZ_BU cells per thread per round, loads grouped by dependency level (winner -> accumulator) so that a
-            // round costs two L2 round trips instead of 2 * FZ_BU
+            // FZ_BU cells per thread per round, loads grouped by dependency level (winner -> accumulator), and the winners
+            // of the NEXT round requested before this round's accumulator loads: one L2 round trip per round
             int slot[FZ_BU];
             float xv[FZ_BU][4];
             float4 a[FZ_BU];
             float cn[FZ_BU];
 #pragma unroll
             for (int u = 0; u < FZ_BU; ++u) {
-                const int ci = c0 + u * FZ_THREADS;
-                slot[u] = ci < s1 ? __ldcg(wf + ci) : -2;
+                slot[u] = slot_next[u];
+                const int cn_i = c0 + (FZ_BU + u) * FZ_THREADS;
+                slot_next[u] = cn_i < s1 ? __ldcg(wf + cn_i) : -2;
             }
 #pragma unroll
             for (int u = 0; u < FZ_BU; ++u) {
@@ -767,11 +877,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) xv[u][ch] = XIo<XT>::ld(xf + (long long)ch * n + ci);
             }
-            if (staged && P.adain) {
+            if (P.adain) {
 #pragma unroll
                 for (int u = 0; u < FZ_BU; ++u) {
                     const int ci = c0 + u * FZ_THREADS;
-                    if (ci < s1) sx4[ci - s0] = make_float4(xv[u][0], xv[u][1], xv[u][2], xv[u][3]);
+                    if (ci < s1 && soff + ci < smem_cells) sx4[soff + ci] = make_float4(xv[u][0], xv[u][1], xv[u][2], xv[u][3]);
                 }
             }
 #pragma unroll
@@ -781,7 +891,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
                 if (slot[u] >= 0) {
                     if (xchg) {                       // the owner's record of this step (remote for foreign slots)
                         const int o = slot[u] / slice;
-                        const FzRec r = fz_rec_wait(P.peers[o] + P.ll_off + (long long)(slot[u] - o * slice) * 32, epoch);
+                        const FzRec r = fz_rec_wait(P.peers[o] + P.ll_off + (long long)(slot[u] - o * slice) * 32, epoch, P.status);
                         a[u] = r.s;
                         cn[u] = r.c;
                     } else {
@@ -817,7 +927,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             }
         }
         if (!P.adain) continue;
-        FZ_TRACE(5);
         {
             const double v = fz_warp_sum16(sums, lane);
             // lane pair (2q, 2q+1) holds value index j with bits: j3 = lane bit 4, j2 = bit 3, j1 = bit 2, j0 = bit 1
@@ -825,54 +934,104 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
             if ((lane & 1) == 0) red[warp * 16 + j] = v;
         }
         __syncthreads();
-        double *fs = stats + (long long)f * 16;
         if (tid < 16) {
             double v = 0.0;
             for (int k = 0; k < FZ_THREADS / 32; ++k) v += red[k * 16 + tid];
-            if (grp > 1) atomicAdd(fs + tid, v);
-            else red[tid] = v;                         // warp 0 only reads rows written before the barrier above
+            red[tid] = v;                              // thread t only ever touches column t of the scratch rows
         }
-        if (grp > 1) {                                 // the frame's CTAs meet at the frame's own counter
-            fz_fence_gpu();
+        if (warp == 0) {
+            __syncwarp();
+            if (lane < 6) {
+                const double va = red[3 * lane], vb = lane < 5 ? red[3 * lane + 1] : 0.0, vc = lane < 5 ? red[3 * lane + 2] : 0.0;
+                fz_stat_store(slots + ((long long)(blockIdx.x + f) * 6 + lane) * 32, va, vb, vc, epoch);
+            }
+        }
+        __syncthreads();                               // the scratch is reused by the next segment
+    }
+    FZ_TRACE(5);
+    if (P.adain) {
+        for (long long p0 = beg; p0 < end;) {
+            const int f = (int)(p0 / n);
+            const int s0 = (int)(p0 - (long long)f * n);
+            const int s1 = (int)min((long long)n, end - (long long)f * n);
+            const long long soff = p0 - beg - s0;
+            p0 += s1 - s0;
+            XT *xf = x + (long long)f * 4 * n;
+            if (warp == 0) {
+                // the CTAs that own a piece of frame f: c_lo holds its first cell, c_hi its last
+                const long long fa = (long long)f * n, fb = fa + n - 1;
+                int c_lo, c_hi;
+                if (grp) { c_lo = f * grp; c_hi = c_lo + grp - 1; }
+                else {
+                    c_lo = (int)((fa * G) / NC), c_hi = (int)((fb * G) / NC);
+                    while (c_lo + 1 < G && cta_start(c_lo + 1) <= fa) ++c_lo;
+                    while (c_lo > 0 && cta_start(c_lo) > fa) --c_lo;
+                    while (c_hi + 1 < G && cta_start(c_hi + 1) <= fb) ++c_hi;
+                    while (c_hi > 0 && cta_start(c_hi) > fb) --c_hi;
+                }
+                // lanes 0..29: five CTAs at a time, record r6 = lane % 6 of CTA c_lo + lane / 6 (+ 5 per round)
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                if (lane < 30) {
+                    const int r6 = lane % 6;
+                    for (int q = c_lo + lane / 6; q <= c_hi; q += 5) {
+                        if (cta_start(q) >= cta_start(q + 1)) continue;       // a CTA without cells publishes nothing
+                        const char *src = slots + ((long long)(q + f) * 6 + r6) * 32;
+                        double va, vb, vc;
+                        unsigned spins = 0;
+                        while (fz_stat_load(src, va, vb, vc) != epoch) {
+                            if (++spins > FZ_SPIN_FAST) {
+                                __nanosleep(500);
+                                if (spins > FZ_SPIN_FAST + FZ_SPIN_LIMIT || *reinterpret_cast<volatile int *>(P.status + FZ_ST_TIMEOUT)) {
+                                    atomicOr(P.status + FZ_ST_TIMEOUT, 1);
+                                    break;
+                                }
+                            }
+                        }
+                        a0 += va; a1 += vb; a2 += vc;
+                    }
+                }
+                // fold the five lane groups: lanes r6, r6 + 6, ..., r6 + 24 hold partial sums of the same three values
+                double *fold = red + 32;                   // [5][18] doubles of the scratch
+                if (lane < 30) { fold[lane * 3] = a0; fold[lane * 3 + 1] = a1; fold[lane * 3 + 2] = a2; }
+                __syncwarp();
+                if (lane < 4) {
+                    double q4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double v = 0.0;
+                        for (int g5 = 0; g5 < 5; ++g5) v += fold[g5 * 18 + lane * 4 + j];
+                        q4[j] = v;
+                    }
+                    const double sx = q4[0], sxx = q4[1], sb = q4[2], sbb = q4[3];
+                    // unbiased variance + 1e-5, sqrt (math_utils.py:39-47); 1/n and 1/(n-1) come from the host in double
+                    coef[lane * 4 + 0] = (float)(sx * P.inv_n);
+                    coef[lane * 4 + 1] = __fsqrt_rn(__fadd_rn((float)((sxx - sx * sx * P.inv_n) * P.inv_nm1), 1e-5f));
+                    coef[lane * 4 + 2] = __fsqrt_rn(__fadd_rn((float)((sbb - sb * sb * P.inv_n) * P.inv_nm1), 1e-5f));
+                    coef[lane * 4 + 3] = (float)(sb * P.inv_n);
+                }
+            }
             __syncthreads();
-            if (tid == 0) {   // the fence above already ordered this CTA's sums: a relaxed arrival is enough
-                asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(fcount + f), "r"(1u) : "memory");
-                const unsigned tgt = epoch * (unsigned)grp;
-                while ((int)(ld_relaxed(fcount + f, false) - tgt) < 0) { }   // the sums are read with ld.cg below
-            }
-        }
-        __syncthreads();
-        if (tid < 4) {
-            double sx, sxx, sb, sbb;
-            if (grp > 1) { sx = __ldcg(fs + tid * 4); sxx = __ldcg(fs + tid * 4 + 1); sb = __ldcg(fs + tid * 4 + 2); sbb = __ldcg(fs + tid * 4 + 3); }
-            else { sx = red[tid * 4]; sxx = red[tid * 4 + 1]; sb = red[tid * 4 + 2]; sbb = red[tid * 4 + 3]; }
-            // unbiased variance + 1e-5, sqrt (math_utils.py:39-47); 1/n and 1/(n-1) come from the host in double
-            coef[tid * 4 + 0] = (float)(sx * P.inv_n);
-            coef[tid * 4 + 1] = __fsqrt_rn(__fadd_rn((float)((sxx - sx * sx * P.inv_n) * P.inv_nm1), 1e-5f));
-            coef[tid * 4 + 2] = __fsqrt_rn(__fadd_rn((float)((sbb - sb * sb * P.inv_n) * P.inv_nm1), 1e-5f));
-            coef[tid * 4 + 3] = (float)(sb * P.inv_n);
-        }
-        __syncthreads();
-        FZ_TRACE(6);
+            FZ_TRACE(6);
 #pragma unroll 4
-        for (int ci = s0 + tid; ci < s1; ci += FZ_THREADS) {
-            float v[4];
-            if (staged) {
-                const float4 t = sx4[ci - s0];
-                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-            } else {
+            for (int ci = s0 + tid; ci < s1; ci += FZ_THREADS) {
+                float v[4];
+                if (soff + ci < smem_cells) {
+                    const float4 t = sx4[soff + ci];
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                } else {
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) v[ch] = XIo<XT>::ld(xf + (long long)ch * n + ci);
-            }
+                    for (int ch = 0; ch < 4; ++ch) v[ch] = XIo<XT>::ld(xf + (long long)ch * n + ci);
+                }
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                // ((x - mu_c) / sigma_c) * sigma_s + mu_s : one rounding per op (math_utils.py:78-80)
-                XIo<XT>::st(xf + (long long)ch * n + ci,
-                            __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(v[ch], coef[ch * 4 + 0]), coef[ch * 4 + 1]), coef[ch * 4 + 2]),
-                                      coef[ch * 4 + 3]));
+                for (int ch = 0; ch < 4; ++ch) {
+                    // ((x - mu_c) / sigma_c) * sigma_s + mu_s : one rounding per op (math_utils.py:78-80)
+                    XIo<XT>::st(xf + (long long)ch * n + ci,
+                                __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(v[ch], coef[ch * 4 + 0]), coef[ch * 4 + 1]), coef[ch * 4 + 2]),
+                                          coef[ch * 4 + 3]));
+                }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
     FZ_TRACE(7);
     if (tid == 0) {
@@ -1091,7 +1250,14 @@ extern "C" int srx_plan_set_grid(srx_plan *p, int ctas) {
     SRX_REQUIRE(ctas >= 0 && ctas <= srx_sm_count_cached(), SRX_ERR_INVALID, "grid must be between 0 and the SM count");
     p->fused_grid = ctas;
     p->cache_ready = false;   // the cached plan is laid out per CTA
-    if (p->ws) SRX_CUDA_CHECK(cudaMemset(p->ws + p->ctrl_off + 8, 0, 8));   // ticket counter + streaming-step count depend on the grid
+    if (p->ws) {
+        // Barrier targets, the accumulator parity, the ticket counter and the statistics records all derive from the
+        // device-side step counter times the grid: restart them together (device idle; in a frame-sharded run every rank
+        // must do the same before any of them steps again).
+        SRX_CUDA_CHECK(cudaDeviceSynchronize());
+        SRX_CUDA_CHECK(cudaMemset(p->ws, 0, (size_t)(p->ll_off + p->ll_bytes)));
+        SRX_CUDA_CHECK(cudaMemset(p->ws + p->stats_off, 0, (size_t)p->stats_bytes));
+    }
     return SRX_OK;
 }
 

@@ -615,10 +615,13 @@ extern "C" int srx_plan_destroy(srx_plan *p) {
 
 extern "C" int srx_plan_check(srx_plan *p, void *stream) {
     SRX_REQUIRE(p && p->ws, SRX_ERR_INVALID, "plan has no workspace");
-    int st_host[2] = {0, 0};
+    int st_host[4] = {0, 0, 0, 0};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     SRX_CUDA_CHECK(cudaMemcpyAsync(st_host, p->ws + p->status_off, sizeof(st_host), cudaMemcpyDeviceToHost, st));
     SRX_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (st_host[2])   // FZ_ST_TIMEOUT of the persistent step kernel (srx_fused.cu)
+        return srx_set_error(SRX_ERR_PEER_LOST, "a wait inside the step kernel gave up after ~2 s: a peer rank (or a CTA group) never "
+                             "arrived — ranks out of step, a dead peer, or unequal grids; the latents of that step are invalid");
     if (st_host[ST_CELL_RANGE])
         return srx_set_error(SRX_ERR_INDEX, "index out of range: a valid id pixel maps outside the latent");
     if (st_host[ST_KEY_RANGE])

@@ -63,9 +63,9 @@ static inline void plan_layout(srx_plan *p) {
     off = align_up(off + p->winner64_bytes, 256);
     p->status_off = off;
     off += 256;
-    p->stats_off = off;  // [2][batch][16] double: per-frame AdaIN sums of the persistent step kernel (double buffered),
-                         // then [batch] u32 per-frame arrival counters (monotonic)
-    p->stats_bytes = (int64_t)2 * d.batch * 16 * 8 + (int64_t)d.batch * 4;
+    p->stats_off = off;  // [<= 1024 CTAs + batch][6] statistics records of 32 B {3 doubles, step}: the AdaIN partial sums of
+                         // (CTA c, frame f) live in slot c + f; exchanged between the CTAs that share a latent frame
+    p->stats_bytes = ((int64_t)1024 + d.batch) * 6 * 32;
     off = align_up(off + p->stats_bytes, 256);
     p->need_off = off;   // [K] byte map of winner keys (cached plan); bytes so that ranks can combine theirs with a MAX all-reduce
     off = align_up(off + p->kcap, 256);

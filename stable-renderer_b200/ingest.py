@@ -78,9 +78,69 @@ class FrameIngest:
         return self._n
 
     def clear(self):
-        """`data_to_be_added_to_engineData.clear()` after a prompt was submitted (renderManager.py:1025)."""
+        """`data_to_be_added_to_engineData.clear()` after a prompt was submitted (renderManager.py:1025).  The batches handed
+        out through `data` stay valid (the reference builds EngineData from its own `torch.cat` results): the next frames go
+        into a fresh set of buffers instead of overwriting tensors a sampling run may still be reading."""
+        if self._n:
+            self._buf = {k: torch.empty(s, dtype=d, device=self.device) for k, (s, d) in self._shapes(self._cap).items()}
         self._n = 0
         self.frame_indices = []
+
+    def _array_handle(self, a):
+        """cudaArray_t of an attachment: a `Texture` (mapped here, unmapped by `unmap_all`), or a raw handle (int)."""
+        if a is None:
+            return None
+        if hasattr(a, "map_array"):
+            return a.map_array()
+        return int(a)
+
+    def save_frame_arrays(self, frame_count: int, color, ids, pos=None, normal_depth=None, noise=None, canny=None,
+                          flip: bool = True, canny_dtype: torch.dtype = torch.float32):
+        """Zero-copy form of `save_frame_data`: the attachments are the mapped cudaArrays of the GL textures (`Texture`
+        objects of this package, or raw `cudaArray_t` handles) and the ingest kernel reads them through surface objects —
+        no staging tensor per attachment, no device-wide sync, no flip pass (replaces the seven `Texture.tensor()` reads of
+        renderManager.py:882-943).  Arrays keep the GL row order, hence `flip=True` by default."""
+        H, W, dev = self.height, self.width, self.device
+        if color is None or ids is None:
+            raise ValueError("the colour and id attachments are required")
+        if canny is not None and canny_dtype != self._canny_dtype:
+            if self._n or canny_dtype not in (torch.float16, torch.float32):
+                raise ValueError(f"canny must be {self._canny_dtype} like the frames collected so far")
+            self._canny_dtype = canny_dtype
+            self._buf["canny_maps"] = torch.empty(self._shapes(self._cap)["canny_maps"][0], dtype=canny_dtype, device=dev)
+        if self._n == self._cap:
+            self._reserve(self._cap * 2)
+        textures = [t for t in (color, ids, pos, normal_depth, noise, canny) if hasattr(t, "map_array")]
+        try:
+            arr = _lib.srx_gbuffer_arrays(self._array_handle(color), self._array_handle(ids), self._array_handle(pos),
+                                          self._array_handle(normal_depth), self._array_handle(noise), self._array_handle(canny),
+                                          _lib.torch_dtype_code(self._canny_dtype))
+            a = _lib.srx_ingest_args()
+            a.height, a.width, a.flip_rows, a.frame_slot = H, W, int(bool(flip)), self._n
+            self._fill_outputs(a, pos is not None, normal_depth is not None, canny is not None, noise is not None)
+            with torch.cuda.device(dev):
+                _lib.check(self._lib.srx_frame_ingest_arrays(C.byref(a), C.byref(arr), _lib.current_stream_ptr(dev)))
+        finally:
+            for t in textures:
+                t.unmap_array()
+        self.frame_indices.append(int(frame_count))
+        self._n += 1
+
+    def _fill_outputs(self, a, has_pos: bool, has_nd: bool, has_canny: bool, has_noise: bool):
+        b, n = self._buf, self._n
+        a.bg_noise = self.GlobalBGNoise.data_ptr() if has_noise else None
+        a.color_maps, a.masks, a.id_maps = b["color_maps"].data_ptr(), b["masks"].data_ptr(), b["id_maps"].data_ptr()
+        a.pos_maps = b["pos_maps"].data_ptr() if has_pos else None
+        a.normal_maps = b["normal_maps"].data_ptr() if has_nd else None
+        a.depth_maps = b["depth_maps"].data_ptr() if has_nd else None
+        a.canny_maps = b["canny_maps"].data_ptr() if has_canny else None
+        a.noise_maps = b["noise_maps"].data_ptr() if has_noise else None
+        a.workspace, a.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        # an attachment that is absent for this frame leaves zeros in its slot, not uninitialised memory
+        for key, present in (("pos_maps", has_pos), ("normal_maps", has_nd), ("depth_maps", has_nd), ("canny_maps", has_canny),
+                             ("noise_maps", has_noise)):
+            if not present:
+                b[key][n].zero_()
 
     def save_frame_data(self, frame_count: int, color: torch.Tensor, ids: torch.Tensor, pos: Optional[torch.Tensor] = None,
                         normal_depth: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
@@ -107,15 +167,7 @@ class FrameIngest:
         a.src = _lib.srx_gbuffer(_ptr(color), _ptr(ids), _ptr(pos), _ptr(normal_depth), _ptr(noise), _ptr(canny),
                                  _lib.torch_dtype_code(self._canny_dtype))
         a.height, a.width, a.flip_rows, a.frame_slot = H, W, int(bool(flip)), self._n
-        b = self._buf
-        a.bg_noise = self.GlobalBGNoise.data_ptr() if noise is not None else None
-        a.color_maps, a.masks, a.id_maps = b["color_maps"].data_ptr(), b["masks"].data_ptr(), b["id_maps"].data_ptr()
-        a.pos_maps = b["pos_maps"].data_ptr() if pos is not None else None
-        a.normal_maps = b["normal_maps"].data_ptr() if normal_depth is not None else None
-        a.depth_maps = b["depth_maps"].data_ptr() if normal_depth is not None else None
-        a.canny_maps = b["canny_maps"].data_ptr() if canny is not None else None
-        a.noise_maps = b["noise_maps"].data_ptr() if noise is not None else None
-        a.workspace, a.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        self._fill_outputs(a, pos is not None, normal_depth is not None, canny is not None, noise is not None)
         with torch.cuda.device(dev):
             _lib.check(self._lib.srx_frame_ingest(C.byref(a), _lib.current_stream_ptr(dev)))
         self.frame_indices.append(int(frame_count))
@@ -177,6 +229,26 @@ class GBufferTemp:
         with torch.cuda.device(dev):
             _lib.check(self._lib.srx_gbuffer_merge_closer(C.byref(cur), H, W, int(bool(flip)), C.byref(tmp),
                                                           _lib.current_stream_ptr(dev)))
+
+    def merge_closer_arrays(self, color, ids, pos, normal_depth, noise, canny, flip: bool = True,
+                            canny_dtype: torch.dtype = torch.float32):
+        """`merge_closer` reading the mapped cudaArrays of the attachments (`Texture` objects or raw `cudaArray_t` handles)."""
+        if normal_depth is None:
+            raise ValueError("the normal+depth attachment is required")
+        H, W, dev = self.height, self.width, self.device
+        srcs = (color, ids, pos, normal_depth, noise, canny)
+        textures = [t for t in srcs if hasattr(t, "map_array")]
+        try:
+            h = [None if t is None else (t.map_array() if hasattr(t, "map_array") else int(t)) for t in srcs]
+            cur = _lib.srx_gbuffer_arrays(h[0], h[1], h[2], h[3], h[4], h[5], _lib.torch_dtype_code(canny_dtype))
+            tmp = _lib.srx_gbuffer_temp(self.color.data_ptr(), self.ids.data_ptr(), self.pos.data_ptr(), self.normal.data_ptr(),
+                                        self.depth.data_ptr(), self.noise.data_ptr(), self.canny.data_ptr())
+            with torch.cuda.device(dev):
+                _lib.check(self._lib.srx_gbuffer_merge_closer_arrays(C.byref(cur), H, W, int(bool(flip)), C.byref(tmp),
+                                                                     _lib.current_stream_ptr(dev)))
+        finally:
+            for t in textures:
+                t.unmap_array()
 
 
 __all__ = ["FrameIngest", "GBufferTemp"]

@@ -341,3 +341,77 @@ def test_fused_peer_exchange_three_ranks_on_one_gpu():
                 plans[r].step(xs[r], 0.5)
         torch.cuda.synchronize()
         assert_close(t2n(torch.cat(xs, dim=0)), t2n(ref), 2e-5, 5e-6, f"3-rank peer exchange, step {step}")
+
+
+def test_fused_adain_flag_may_change_between_steps_of_one_plan():
+    """adain is a per-call flag and plans are shared (cached on the IDMap): steps that skip AdaIN must not leave the
+    statistics exchange of a later AdaIN step waiting (batch < SM count, so several CTAs share a frame)."""
+    from stable_renderer_b200.plan import OverlapPlan
+    ids, x0 = _inputs(4, 256, 256, 128, seed=21)
+    want, parts = O.overlap_step(x0.numpy(), ids.numpy(), None, ratio=0.5, accumulate="f64", return_parts=True)
+    plan = OverlapPlan(ids.cuda(), x0.shape, key_capacity=128 * 128)
+    assert plan.fused
+    for adain in (False, False, True, False, True, True):
+        x = x0.cuda()
+        plan.step(x, 0.5, adain=adain)
+        plan.check()
+        assert_close(t2n(x), want if adain else parts["blended"], RTOL, ATOL, f"adain={adain}")
+
+
+def test_fused_set_grid_after_steps():
+    """Changing the grid of a plan that has already stepped restarts the device-side step counter, barrier counters,
+    accumulators and statistics records together."""
+    from stable_renderer_b200 import _lib
+    from stable_renderer_b200.plan import OverlapPlan
+    sms = _lib.load().srx_device_sm_count()
+    ids, x0 = _inputs(5, 256, 256, 128, seed=23)
+    want = O.overlap_step(x0.numpy(), ids.numpy(), None, ratio=0.5, accumulate="f64")
+    plan = OverlapPlan(ids.cuda(), x0.shape, key_capacity=128 * 128)
+    for grid in (0, sms // 2, sms // 3, 0):
+        plan.set_grid(grid)
+        for _ in range(3):       # an odd number of steps leaves the "other" accumulator dirty
+            x = x0.cuda()
+            plan.step(x, 0.5)
+        plan.check()
+        assert_close(t2n(x), want, RTOL, ATOL, f"grid {grid}")
+
+
+def test_fused_lost_peer_raises_instead_of_hanging():
+    """A rank whose peer never steps must not hang inside the cooperative kernel: its waits give up after ~2 s, the step
+    finishes (with invalid latents) and `check()` reports the lost peer."""
+    from stable_renderer_b200 import _lib
+    from stable_renderer_b200.plan import OverlapPlan
+    sms = _lib.load().srx_device_sm_count()
+    ids, x0 = _inputs(4, 128, 128, 64, seed=29)
+    ids = ids.cuda()
+    plans = [OverlapPlan(ids[r * 2:(r + 1) * 2].contiguous(), (2, 4, 16, 16), key_capacity=64 * 64) for r in range(2)]
+    ptrs = [p.workspace.data_ptr() for p in plans]
+    for r, p in enumerate(plans):
+        p.set_grid(sms // 2)
+        p.bind_peers(r, ptrs)
+    x = x0[:2].contiguous().cuda()
+    plans[0].step(x, 0.5)            # rank 1 never steps
+    with pytest.raises(_lib.SrxError, match="never arrived|gave up"):
+        plans[0].check()
+
+
+def test_idmap_invalidate_rebinds_cached_plans_to_the_new_ids():
+    """IDMap.invalidate() with a CPU tensor (the `from_directory` default): the cached plan must stream the NEW ids, in
+    the streaming regime and after re-bucketing."""
+    from helpers import Ctx, EngineData
+    from stable_renderer_b200.corresponder import OverlapCorresponder
+    from stable_renderer_b200.corrmap import IDMap
+    ids_a, x0 = _inputs(4, 256, 256, 128, seed=31)
+    ids_b, _ = _inputs(4, 256, 256, 128, seed=37)
+    host = ids_a.clone()
+    idm = IDMap(tensor=host)
+    ed = EngineData(id_maps=idm)
+    oc = OverlapCorresponder(step_finished_inject_ratio=0.5, key_capacity=128 * 128)
+    for ids in (ids_a, ids_b, ids_a):
+        host.copy_(ids)
+        idm.invalidate()
+        want = O.overlap_step(x0.numpy(), ids.numpy(), None, ratio=0.5, accumulate="f64")
+        for s in range(3):          # step 0 streams, later steps run from the cached plan
+            ctx = Ctx(x0.cuda(), step_index=s, total_steps=3)
+            oc.step_finished(ed, ctx)
+            assert_close(t2n(ctx.noise), want, RTOL, ATOL, f"step {s}")
