@@ -566,7 +566,9 @@ def run_overlap(args, workload: str, rank: int, local: int, world: int, light: b
                           else f"the ids of one step ({id_bytes >> 20} MiB per GPU) are larger than the 126 MB L2"),
                    "kernels": "one persistent kernel per step" if fused_kernel else "split reduce / gather kernels",
                    "parallelism": (f"frames sharded over {world} GPU(s), key accumulator ({acc.numel() * 4 >> 10} KiB) "
-                                   + ("exchanged inside the step kernel over NVLink peer memory (reduce-scatter + all-gather)"
+                                   + (("exchanged inside the step kernel over NVLink: in-switch reduction (multimem.ld_reduce) of the "
+                                       "owner's slice + multicast (multimem.st) of the totals" if getattr(plan, "nvls", False) else
+                                       "exchanged inside the step kernel over NVLink peer memory (pull reduce-scatter + record all-gather)")
                                       if peer else "summed with one NCCL all-reduce between the reduce and gather kernels"))
                    if world > 1 else "single GPU"},
         "overlap_steps_per_sec": 1e3 / ms_step,

@@ -119,6 +119,11 @@ int srx_plan_bind_workspace(srx_plan *plan, void *workspace_dev, int64_t bytes, 
  * frames, exchanges the key accumulator with the peers over NVLink inside the same kernel, and gathers this rank's
  * frames; every rank must call it the same number of times.  world = 1 unbinds. */
 int srx_plan_bind_peers(srx_plan *plan, int rank, int world, void *const *peer_workspaces);
+/* NVLS form of the in-kernel exchange: `mc_ws` = the multicast address of the symmetric workspace (one pointer that reaches
+ * every rank's copy through the NVSwitch).  The owner then receives its slice reduced inside the switch (multimem.ld_reduce)
+ * and broadcasts the totals (multimem.st); every rank gathers from its LOCAL record table.  All ranks or none; after
+ * srx_plan_bind_peers; NULL = back to the pull exchange. */
+int srx_plan_bind_multicast(srx_plan *plan, void *mc_ws);
 /* Bucketing pass for the cached-plan regime (steps 2..N of a sampling run reuse the ids).  Replaces what the
  * reference recomputes every step — `unique(return_inverse)` over the [N] key column (math_utils.py:137) — by one pass
  * per id batch.  Call twice: with pool_dev == NULL it streams the ids once (per-cell winners, the set of keys that win a
@@ -195,18 +200,21 @@ int srx_ids_rank_table(const void *ids_dev, int id_dtype, int frames, int height
 int srx_group_broadcast(const float *table_dev, const int32_t *rank_dev, int64_t n, int channels, float *out_dev, void *stream);
 
 typedef struct srx_noise_args {
-    const void *ids_dev;          /* [F,H,W,4]; H, W must equal the node's 512 / 1024 working size */
+    const void *ids_dev;          /* [F,H,W,4] */
     int id_dtype;
     int frames, height, width;
-    const int32_t *inv_frame_dev; /* [F] id frame that writes latent frame f, or -1 (inverse of IDMap.frame_indices) */
+    const int32_t *inv_frame_dev; /* [F] LAST id frame that writes latent frame f, or -1 (inverse of IDMap.frame_indices) */
     const int32_t *rank_table_dev;/* from srx_ids_rank_table */
     const float *key_latent_dev;  /* [n_unique,4] random row per key for the latent (mode 0 only) */
     const float *key_noise_dev;   /* [n_unique,4] random row per key for the noise */
-    const float *base_latent_dev; /* [4,H,W] the node's base latent draw (mode 0 only) */
-    const float *base_noise_dev;  /* [4,H,W] */
-    float *latent_out_dev;        /* mode 0: [F,4,H/8,W/8] */
-    float *noise_out_dev;         /* mode 0: [F,4,H/8,W/8]; modes 1-3: F*4*H*W/32 floats (the node views them as [2F,4,H/8,W/8]) */
+    const float *base_latent_dev; /* [4,S,S] the node's base latent draw (mode 0 only) */
+    const float *base_noise_dev;  /* [4,S,S] */
+    float *latent_out_dev;        /* mode 0: [F,4,S/8,S/8] */
+    float *noise_out_dev;         /* mode 0: [F,4,S/8,S/8]; modes 1-3: F*4*S*S/32 floats (the node views them as [2F,4,S/8,S/8]) */
     int mode;                     /* downsample_option: 0 nearest, 1 mean, 2 max, 3 min (loaders.py:252-268) */
+    int work_size;                /* S = the node's working size (512 SD15 / 1024 SDXL); 0 = the id map's own (square) size.  Entry
+                                     (x, y) lands in pixel (trunc(fl32(x/H)*S), trunc(fl32(y/W)*S)), loaders.py:218-219 */
+    const int32_t *prev_frame_dev;/* [F] the previous id frame writing the same latent frame as id frame g, or -1; NULL = none */
 } srx_noise_args;
 int srx_noise_from_ids(const srx_noise_args *args, void *stream);
 
@@ -245,6 +253,13 @@ int srx_legacy_overlap(const srx_legacy_desc *desc, const srx_legacy_args *args,
  * srx_legacy_overlap (radius 0 gives the same result as srx_legacy_overlap, more slowly); its own, larger workspace. */
 int64_t srx_legacy_ordered_workspace_bytes(const srx_legacy_desc *desc);
 int srx_legacy_overlap_ordered(const srx_legacy_desc *desc, const srx_legacy_args *args, int kernel_radius, void *stream);
+
+/* johnny_overlap (legacy_codes/legacy_diffuser/modules/diffuser_pipelines/overlap/johnny_overlap.py:15-141), the diffusers
+ * pipeline's experimental variant: frame-distance weights 1/(|dt|+1), every entry of a trace updated IN PLACE before the next
+ * one is evaluated, optional mix with a base colour taken at the trace's first entry (`beta`; base_dev = [T, B*C, h, w] float32
+ * noised original latents), nearest up- / down-sampling without the `where`.  desc->strategy is ignored; workspace =
+ * srx_legacy_ordered_workspace_bytes(). */
+int srx_johnny_overlap(const srx_legacy_desc *desc, const srx_legacy_args *args, float beta, const float *base_dev, void *stream);
 
 /* CorrespondenceMap maintenance (legacy data_classes/correspondence_map.py).  The map IS the id buffers: a key is the id
  * tuple (after merge_nearby's floor division), deleting a key clears the ids of every pixel that carries it.
@@ -419,6 +434,34 @@ int srx_gbuffer_merge_closer_arrays(const srx_gbuffer_arrays *cur, int height, i
                                     void *stream);
 /* Where cur's reversed depth > temp->depth, every attachment of the pixel replaces the stored one (in place). */
 int srx_gbuffer_merge_closer(const srx_gbuffer *cur, int height, int width, int flip_rows, const srx_gbuffer_temp *temp, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Wide-channel feature overlap — the body of OverlapCorresponder.post_atten_inject
+ * (source/common_utils/stable_render_utils/corresponder.py:236-295; dead in the reference behind `return origin_values`, :228):
+ * group mean of the [B, h*w, c] post-attention features by vertex id through nearest up-sampling to (map_height, map_width),
+ * blend with `ratio`, last-writer write-back, nearest down-sampling, AdaIN of the original features to the result's
+ * per-(frame, channel) statistics.  (map_height, map_width) = (IDMap.height, IDMap.width) in the reference, which for
+ * [F,H,W,4] ids are (W, 4) — corrmap.py:85-93 — the caller decides.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct srx_feature_args {
+    const void *ids_dev;        /* [F,H,W,4] */
+    int id_dtype;               /* SRX_I32 | SRX_I16 */
+    int frames, height, width;
+    const int32_t *frame_map_dev; /* DEVICE [F]: batch index of every id frame (IDMap.frame_indices, corresponder.py:254) */
+    const void *feat_dev;       /* [B, h*w, c], contiguous */
+    void *out_dev;              /* [B, h*w, c], same dtype (may not alias feat_dev) */
+    int x_dtype;                /* SRX_F32 | SRX_F16 | SRX_BF16 (computed in fp32, rounded once) */
+    int batch, lat_h, lat_w, channels;   /* c <= 1280, c * element size a multiple of 16 bytes */
+    int map_height, map_width;
+    float ratio;                /* post_attn_inject_ratio (corresponder.py:176, default 0.6) */
+    int64_t key_capacity;       /* vertex ids must be < key_capacity */
+    void *workspace;            /* srx_feature_overlap_workspace_bytes(), 256-byte aligned */
+    int64_t workspace_bytes;
+} srx_feature_args;
+int64_t srx_feature_overlap_workspace_bytes(const srx_feature_args *args);
+int srx_feature_overlap(const srx_feature_args *args, void *stream);
+/* SRX_ERR_INDEX / SRX_ERR_KEY_RANGE for device-side failures of the last call on this workspace (syncs) */
+int srx_feature_overlap_check(const srx_feature_args *args, void *stream);
 
 #ifdef __cplusplus
 }

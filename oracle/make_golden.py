@@ -463,6 +463,98 @@ def node_cases():
     save("node_samplers", legacy_ids=ids.numpy(), legacy_latents=lat.numpy(), ids=ids_c.numpy(), latents=x.numpy(), **out)
 
 
+def feature_cases(R):
+    """§8f-4: the post_atten_inject body (early return bypassed, ref_shim.post_atten_inject_body) on [B, hw, c] features with
+    the reference's own (quirky) up-sampling size (IDMap.height, IDMap.width) = (W, 4), and taichi_cells_overlap run as Python."""
+    body = ref_shim.post_atten_inject_body()
+    IDMap = R["corrmap"].IDMap
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    for tag, (F, H, hw, c) in (("a", (3, 64, 64, 40)), ("b", (2, 96, 144, 24))):
+        ids = synthetic.make_ids(F, H, H, tex_h=32, tex_w=32, frac_2048=0.05, seed=51)
+        feats = torch.randn(F, hw, c, generator=g)
+        oc = R["corresponder"].OverlapCorresponder(post_attn_inject_ratio=0.6)
+        with ref_shim.quiet():
+            res = body(oc, None, _EngineData(IDMap(tensor=ids.clone())), feats.clone(), 12)
+        out[f"ids_{tag}"], out[f"features_{tag}"], out[f"out_{tag}"] = ids.numpy(), feats.numpy(), res.numpy()
+    # cell-similarity overlap: 2 frames of 8x8 pixels, 16 cells of 4 consecutive pixels, 6-wide values
+    fn = ref_shim.taichi_cells_overlap_python()
+    idc = synthetic.make_ids(2, 8, 8, tex_h=3, tex_w=3, seed=52).reshape(2, 64, 4).float()
+    vals = torch.randn(2, 16, 6, generator=g)
+    contrib = torch.rand(2, 64, generator=g) * 0.25
+    new = torch.zeros_like(vals)
+    fn(idc, vals, new, contrib)
+    out["cells_ids"], out["cells_values"], out["cells_contrib"], out["cells_new"] = idc.numpy(), vals.numpy(), contrib.numpy(), new.numpy()
+    save("feature_overlap", ratio=np.float64(0.6), **out)
+
+
+def johnny_cases(R):
+    """L7: johnny_overlap.overlap (ref_shim.johnny_overlap_function: the one broken statement replaced) on a 4-frame map."""
+    fn = ref_shim.johnny_overlap_function()
+    CorrespondenceMap = R["correspondence_map"].CorrespondenceMap
+    T, H, W, h, w = 4, 32, 32, 4, 4
+    ids = synthetic.make_ids(T, H, W, tex_h=16, tex_w=16, seed=71, legacy_layout=True, dtype=torch.int16)
+    with tempfile.TemporaryDirectory() as td:
+        iddir = os.path.join(td, "id")
+        os.makedirs(iddir)
+        for f in range(T):
+            np.save(os.path.join(iddir, f"id_{f}.npy"), ids[f].numpy())
+        with ref_shim.quiet():
+            cmap = CorrespondenceMap.FromExisting(iddir, enable_cache=False)
+    assert len(cmap.Map) >= 100, "the reference's progress bar divides by len(Map) // 100"
+    g = torch.Generator().manual_seed(9)
+    frames = [torch.randn(1, 4, h, w, generator=g, dtype=torch.float64) for _ in range(T)]
+    orig = [torch.randn(1, 4, h, w, generator=g, dtype=torch.float64) for _ in range(T)]
+    noise = [torch.randn(1, 4, h, w, generator=g, dtype=torch.float64) for _ in range(T)]
+
+    class _Sched:
+        @staticmethod
+        def add_noise(lat, nz, t):
+            return lat * 0.8 + nz * 0.6
+
+    class _Pipe:
+        scheduler = _Sched()
+
+    out = {}
+    with ref_shim.quiet():
+        out["out_beta0"] = torch.stack(fn([f.clone() for f in frames], cmap, _Pipe(), step=3, timestep=500)).numpy()
+        out["out_beta03"] = torch.stack(fn([f.clone() for f in frames], cmap, _Pipe(), step=3, timestep=500, init_latents_orig_seq=orig,
+                                           noise_seq=noise, beta=0.3)).numpy()
+        gated = fn([f.clone() for f in frames], cmap, _Pipe(), step=3, timestep=1500)          # timestep > start_timestep: alpha = 0
+    out["gated_is_input"] = np.array(all(torch.equal(a, b) for a, b in zip(gated, frames)))
+    save("johnny_overlap", ids=ids.numpy(), frames=torch.stack(frames).numpy(), orig=torch.stack(orig).numpy(),
+         noise=torch.stack(noise).numpy(), **out)
+
+
+def interp_cases(R):
+    """ResizeOverlap with interpolate_mode != 'nearest' (overlap.py:205-221): the latents really are resampled."""
+    CorrespondenceMap = R["correspondence_map"].CorrespondenceMap
+    ov = R["overlap"]
+    Scheduler = R["overlap_scheduler"].Scheduler
+    factory = R["algorithms"].overlap_algorithm_factory
+    T, H, W, h, w = 4, 32, 32, 4, 4
+    ids = synthetic.make_ids(T, H, W, tex_h=16, tex_w=16, seed=31, legacy_layout=True, dtype=torch.int16)
+    with tempfile.TemporaryDirectory() as td:
+        iddir = os.path.join(td, "id")
+        os.makedirs(iddir)
+        for f in range(T):
+            np.save(os.path.join(iddir, f"id_{f}.npy"), ids[f].numpy())
+        with ref_shim.quiet():
+            cmap = CorrespondenceMap.FromExisting(iddir, enable_cache=False)
+    torch.manual_seed(5)
+    frames = [torch.randn(1, 4, h, w, dtype=torch.float32) for _ in range(T)]
+    alpha_s = Scheduler(interpolate_begin=0.7, interpolate_end=0.7, interpolate_type="constant")
+    rad_s = Scheduler(interpolate_begin=0.0, interpolate_end=0.0, interpolate_type="constant")
+    res = {}
+    for mode in ("bilinear", "bicubic", "area"):
+        for strat in ("average", "frame_distance"):
+            o = ov.ResizeOverlap(alpha_s, rad_s, factory(strat), verbose=False, interpolate_mode=mode)
+            with ref_shim.quiet():
+                outs = o([f.clone() for f in frames], cmap, step=0, timestep=500)
+            res[f"out_{mode}_{strat}"] = torch.stack(outs).numpy()
+    save("legacy_resize_overlap_interp", ids=ids.numpy(), frames=torch.stack(frames).numpy(), alpha=np.float64(0.7), **res)
+
+
 def main():
     if "--only-ingest" in sys.argv:
         torch.set_num_threads(1)
@@ -471,6 +563,18 @@ def main():
     if "--only-latent-init" in sys.argv:
         torch.set_num_threads(1)
         latent_init_cases(ref_shim.load_reference())
+        return
+    if "--only-interp" in sys.argv:
+        torch.set_num_threads(1)
+        interp_cases(ref_shim.load_reference())
+        return
+    if "--only-johnny" in sys.argv:
+        torch.set_num_threads(1)
+        johnny_cases(ref_shim.load_reference())
+        return
+    if "--only-features" in sys.argv:
+        torch.set_num_threads(1)
+        feature_cases(ref_shim.load_reference())
         return
     if "--only-nodes" in sys.argv:
         torch.set_num_threads(1)
@@ -488,6 +592,9 @@ def main():
     legacy_cases(R)
     latent_init_cases(R)
     ingest_cases(R)
+    feature_cases(R)
+    johnny_cases(R)
+    interp_cases(R)
     node_cases()
 
 

@@ -301,3 +301,77 @@ def load_reference_nodes(ksampler) -> dict:
     out["legacy_schedulers"] = _load("legacy_nodes.schedulers", "legacy_codes/nodes/schedulers.py")
     out["samplers"] = _load("ref_nodes.samplers", "source/comfyUI/stable_rendering/_nodes/samplers.py")
     return out
+
+
+def post_atten_inject_body():
+    """The body of ``OverlapCorresponder.post_atten_inject`` with its leading ``return origin_values`` (corresponder.py:228)
+    removed: the reference's own statements for the wide-channel feature overlap, unreachable as shipped.  Returns a function
+    ``f(self, block, engine_data, origin_values, layer)``."""
+    import ast
+    R = load_reference()
+    path = os.path.join(REFERENCE_ROOT, "source/common_utils/stable_render_utils/corresponder.py")
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == "OverlapCorresponder":
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == "post_atten_inject":
+                    assert isinstance(fn.body[0], ast.Return), "the early return is expected to be the first statement"
+                    fn.body = fn.body[1:]
+                    fn.returns = None
+                    for a in fn.args.args:
+                        a.annotation = None
+                    mod = ast.Module(body=[fn], type_ignores=[])
+                    ast.fix_missing_locations(mod)
+                    ns = dict(vars(R["corresponder"]))
+                    exec(compile(mod, path, "exec"), ns)
+                    return ns["post_atten_inject"]
+    raise KeyError("post_atten_inject")
+
+
+def taichi_cells_overlap_python():
+    """``taichi_cells_overlap`` (corr_utils.py:110-134) executed as plain Python: the shim's taichi stand-in makes
+    ``ti.kernel`` / ``ti.func`` identity decorators, so only ``ti.ndrange`` and ``ti.math.ivec2`` need real behaviour."""
+    import itertools
+    R = load_reference()
+    ti = sys.modules["taichi"]
+    ti.ndrange = lambda *ns: itertools.product(*[range(int(n)) for n in ns])
+    m = _StubModule("taichi.math")
+    m.ivec2 = lambda v: list(v) if isinstance(v, (list, tuple)) else v
+    ti.math = m
+    mod = R["corr_utils"]
+    mod.ti = ti
+    return mod.taichi_cells_overlap
+
+
+def johnny_overlap_function():
+    """``johnny_overlap.overlap`` (legacy_diffuser/modules/diffuser_pipelines/overlap/johnny_overlap.py:15-141) with ONE
+    statement changed: ``beta = schedule(step, timestep, 'constant')`` (:38) omits a required argument and raises TypeError as
+    shipped; it becomes ``beta = kwargs.get('beta', 0)``.  Everything else runs as written."""
+    import ast
+    R = load_reference()
+    path = os.path.join(REFERENCE_ROOT, "legacy_codes/legacy_diffuser/modules/diffuser_pipelines/overlap/johnny_overlap.py")
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    patched = 0
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Assign) and len(node.targets) == 1 and getattr(node.targets[0], "id", None) == "beta" \
+                and isinstance(node.value, ast.Call) and getattr(node.value.func, "id", None) == "schedule":
+            node.value = ast.parse("kwargs.get('beta', 0)", mode="eval").body
+            patched += 1
+    assert patched == 1, "expected exactly one `beta = schedule(...)` assignment"
+    ast.fix_missing_locations(tree)
+    pk = "ldiff.modules.diffuser_pipelines.overlap"
+    for name in ("ldiff", "ldiff.modules", "ldiff.modules.diffuser_pipelines", pk, "ldiff.modules.data_classes"):
+        if name not in sys.modules:
+            _stub(name)
+    _stub(pk + ".overlap_scheduler", Scheduler=R["overlap_scheduler"].Scheduler)
+    _stub(pk + ".utils", overlap_rate=lambda *a, **k: 0.0)
+    _stub("ldiff.modules.data_classes.correspondenceMap", CorrespondenceMap=R["correspondence_map"].CorrespondenceMap)
+    mod = types.ModuleType(pk + ".johnny_overlap")
+    mod.__package__ = pk
+    mod.__file__ = path
+    sys.modules[mod.__name__] = mod
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(tree, path, "exec"), mod.__dict__)
+    return mod.overlap

@@ -696,3 +696,131 @@ def gbuffer_merge_closer(temp: Dict[str, np.ndarray], color, ids, pos, normal_de
     temp["pos"][closer] = f(pos)[closer]
     temp["noise"][closer] = f(noise)[closer]
     temp["canny"][closer] = f(canny)[closer].astype(np.float16)
+
+
+# =====================================================================================================
+# §8f-4: wide-channel feature overlap — the body of OverlapCorresponder.post_atten_inject
+# (corresponder.py:236-295; unreachable in the reference behind `return origin_values`, :228) — and the
+# cell-similarity weighting of taichi_cells_overlap (corr_utils.py:110-134)
+# =====================================================================================================
+def feature_overlap(features: np.ndarray, ids: np.ndarray, ratio: float = 0.6, map_height: Optional[int] = None,
+                    map_width: Optional[int] = None, frame_indices: Optional[Sequence[int]] = None,
+                    accumulate: str = "f64", return_parts: bool = False):
+    """features [B, h*w, c] (post-attention values, c = 320..1280) -> [B, h*w, c].
+
+    Statement by statement (corresponder.py:240-295): h = w = sqrt(hw); features to [B,c,h,w]; entry coordinates
+    ``(vsi[:,4] * id_map.width).to(int)``, ``(vsi[:,5] * id_map.height).to(int)``; nearest up-sampling to
+    (id_map.height, id_map.width); gather; group mean keyed by the vertex id; blend with `ratio`; duplicate-index
+    write-back (last entry wins); nearest down-sampling to (h, w); AdaIN(content = features, style = down-sampled).
+
+    NB `IDMap.height` / `IDMap.width` are ``tensor.shape[-2]`` / ``tensor.shape[-1]`` (corrmap.py:85-93), i.e. (W, 4)
+    for the [F,H,W,4] id tensor — the defaults here — not the image size; `map_height` / `map_width` override them."""
+    features = np.asarray(features)
+    B, hw, c = features.shape
+    h = int(round(math.sqrt(hw)))
+    if h * h != hw:
+        raise ValueError(f"Dimension hw={hw} is not a perfect square.")
+    w = h
+    ids = np.asarray(ids)
+    mh = int(ids.shape[-2] if map_height is None else map_height)
+    mw = int(ids.shape[-1] if map_width is None else map_width)
+    feat = features.astype(np.float32).reshape(B, h, w, c)
+    vsi = vertex_screen_info(ids, frame_indices)
+    sx = (vsi[:, 4] * np.float32(mw)).astype(np.int32)
+    sy = (vsi[:, 5] * np.float32(mh)).astype(np.int32)
+    fr = vsi[:, 6].astype(np.int32)
+    if fr.size and (fr.max() >= B or sx.max() >= mw or sy.max() >= mh):
+        raise IndexError("correspondence entry addresses an up-sampled cell out of range")
+    up_y, up_x = nearest_resize_index(mh, h), nearest_resize_index(mw, w)     # up-sampled cell -> feature cell
+    src = (up_y[sy] * w + up_x[sx]).astype(np.int64)                           # feature cell of every entry
+    corr = feat.reshape(B, hw, c)[fr, src]                                     # [N, c]
+    uniq, inv = np.unique(vsi[:, 3], return_inverse=True)
+    inv = inv.reshape(-1)
+    cnt = np.bincount(inv, minlength=uniq.size).astype(np.float32)
+    acc_dt = np.float64 if accumulate == "f64" else np.float32
+    sums = np.zeros((uniq.size, c), dtype=acc_dt)
+    np.add.at(sums, inv, corr.astype(acc_dt))
+    avg = (sums / cnt[:, None].astype(acc_dt)).astype(np.float32)
+    r, one_minus = np.float32(ratio), np.float32(1 - ratio)
+    mixed = one_minus * corr + r * avg[inv]
+    # write-back into the up-sampled tensor: last entry per up-sampled cell wins; then nearest down-sampling
+    ucell = (fr.astype(np.int64) * mh + sy) * mw + sx
+    winner = np.full(B * mh * mw, -1, dtype=np.int64)
+    np.maximum.at(winner, ucell, np.arange(ucell.size, dtype=np.int64))
+    dn_y, dn_x = nearest_resize_index(h, mh), nearest_resize_index(w, mw)     # feature cell -> up-sampled cell it samples
+    Y, X = np.meshgrid(dn_y, dn_x, indexing="ij")
+    style = np.empty((B, h, w, c), dtype=np.float32)
+    for b in range(B):
+        wsel = winner[(b * mh + Y) * mw + X]                                   # [h, w]
+        base = feat[b].reshape(hw, c)[(up_y[Y] * w + up_x[X]).reshape(-1)].reshape(h, w, c)   # the up-sampled value there
+        style[b] = np.where((wsel >= 0)[..., None], mixed[np.maximum(wsel, 0)], base)
+    out = adain(feat.transpose(0, 3, 1, 2), style.transpose(0, 3, 1, 2)).transpose(0, 2, 3, 1).reshape(B, hw, c)
+    if return_parts:
+        return out, dict(style=style.reshape(B, hw, c), winner=winner, src=src, avg=avg, unique_keys=uniq)
+    return out
+
+
+def cells_overlap(id_flatten_maps: np.ndarray, values: np.ndarray, contributions: np.ndarray) -> np.ndarray:
+    """``taichi_cells_overlap`` (corr_utils.py:110-134): every cell becomes the similarity-weighted mean of all cells,
+    ``new[A] = (val[A] + sum_{B != A} sim(A,B) val[B]) / (1 + sum_{B != A} sim(A,B))`` with
+    ``sim(A,B) = sum_{x in A, i in B} contrib[x] contrib[i] [id[x] == id[i]]`` (all four id components, no validity filter:
+    background pixels match each other, :28-44).  A cell is a run of ``pixels // cells`` CONSECUTIVE pixels of the flattened
+    frame (:130).  Restated in the factorised form the GPU kernels use: with ``c_A[key]`` = the summed contribution of A's
+    pixels carrying `key`, ``sim(A,B) = sum_key c_A[key] c_B[key]``."""
+    ids = np.asarray(id_flatten_maps)
+    vals = np.asarray(values, dtype=np.float64)
+    con = np.asarray(contributions, dtype=np.float64)
+    Bn, npx, _ = ids.shape
+    cells = vals.shape[1]
+    cpp = npx // cells
+    used = cells * cpp                                              # trailing pixels belong to no cell
+    _, key = np.unique(ids[:, :used].reshape(-1, ids.shape[-1]), axis=0, return_inverse=True)
+    key = key.reshape(-1)
+    cell = (np.arange(Bn)[:, None] * cells + np.arange(used)[None, :] // cpp).reshape(-1)
+    nkeys, ncells = int(key.max()) + 1, Bn * cells
+    pair = key.astype(np.int64) * ncells + cell
+    up, pinv = np.unique(pair, return_inverse=True)
+    cw = np.bincount(pinv.reshape(-1), weights=con[:, :used].reshape(-1), minlength=up.size)    # c_A[key] per (key, cell) pair
+    pk, pc = up // ncells, up % ncells
+    v = vals.reshape(ncells, -1)
+    S = np.zeros((nkeys, v.shape[1]))
+    np.add.at(S, pk, cw[:, None] * v[pc])
+    T = np.bincount(pk, weights=cw, minlength=nkeys)
+    num = v.copy()
+    den = np.ones(ncells)
+    np.add.at(num, pc, cw[:, None] * (S[pk] - cw[:, None] * v[pc]))
+    np.add.at(den, pc, cw * (T[pk] - cw))
+    return (num / den[:, None]).reshape(vals.shape)
+
+
+# =====================================================================================================
+# L7: johnny_overlap (legacy_diffuser/modules/diffuser_pipelines/overlap/johnny_overlap.py:15-141)
+# =====================================================================================================
+def johnny_overlap(frames: np.ndarray, ids: np.ndarray, alpha: float = 1.0, beta: float = 0.0,
+                   base: Optional[np.ndarray] = None, merge_len: int = 0) -> np.ndarray:
+    """frames [T,B,C,h,w] -> [T,B,C,h,w].  Nearest up-sampling to the map size (:51), per trace (>= 2 entries) every entry i in
+    (frame,row,col) order: ``value = sum_j x_j / (|t_i-t_j|+1)``, ``count = sum_j 1/(|t_i-t_j|+1)`` over the CURRENT values
+    of the trace (earlier entries already rewritten, :95-118), ``x_i = alpha*value/count + (1-alpha)*x_i``, then
+    ``x_i = beta*base_first + (1-beta)*x_i`` with the base colour at the trace's first entry (:112-116); nearest
+    down-sampling (:132).  `base` [T,B,C,h,w] = the noised original latents (:63-65)."""
+    frames = np.asarray(frames, dtype=np.float64)
+    T, B, C, h, w = frames.shape
+    H, W = ids.shape[1], ids.shape[2]
+    uy, ux = nearest_resize_index(H, h), nearest_resize_index(W, w)
+    up = frames[:, :, :, uy][:, :, :, :, ux].copy()
+    up_base = None if base is None or beta <= 0 else np.asarray(base, dtype=np.float64)[:, :, :, uy][:, :, :, :, ux]
+    for trace in correspondence_traces(ids[:T], merge_len).values():
+        L = len(trace)
+        if L == 1:
+            continue
+        fs = np.array([t[2] for t in trace])
+        for i, (y, x, f) in enumerate(trace):
+            wgt = 1.0 / (np.abs(fs - f) + 1.0)
+            cur = np.stack([up[tf, :, :, ty, tx] for (ty, tx, tf) in trace])        # [L,B,C], current values
+            ov = alpha * (np.tensordot(wgt, cur, axes=(0, 0)) / wgt.sum()) + (1 - alpha) * up[f, :, :, y, x]
+            if up_base is not None:
+                y0, x0, f0 = trace[0]
+                ov = beta * up_base[f0, :, :, y0, x0] + (1 - beta) * ov
+            up[f, :, :, y, x] = ov
+    dy, dx = nearest_resize_index(h, H), nearest_resize_index(w, W)
+    return up[:, :, :, dy][:, :, :, :, dx]

@@ -62,7 +62,8 @@ class srx_noise_args(C.Structure):
     _fields_ = [("ids_dev", C.c_void_p), ("id_dtype", C.c_int), ("frames", C.c_int), ("height", C.c_int), ("width", C.c_int),
                 ("inv_frame_dev", C.c_void_p), ("rank_table_dev", C.c_void_p), ("key_latent_dev", C.c_void_p),
                 ("key_noise_dev", C.c_void_p), ("base_latent_dev", C.c_void_p), ("base_noise_dev", C.c_void_p),
-                ("latent_out_dev", C.c_void_p), ("noise_out_dev", C.c_void_p), ("mode", C.c_int)]
+                ("latent_out_dev", C.c_void_p), ("noise_out_dev", C.c_void_p), ("mode", C.c_int), ("work_size", C.c_int),
+                ("prev_frame_dev", C.c_void_p)]
 
 
 class srx_bake_args(C.Structure):
@@ -87,6 +88,14 @@ class srx_ingest_args(C.Structure):
                 ("noise_maps", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
+class srx_feature_args(C.Structure):
+    _fields_ = [("ids_dev", C.c_void_p), ("id_dtype", C.c_int), ("frames", C.c_int), ("height", C.c_int), ("width", C.c_int),
+                ("frame_map_dev", C.c_void_p), ("feat_dev", C.c_void_p), ("out_dev", C.c_void_p), ("x_dtype", C.c_int),
+                ("batch", C.c_int), ("lat_h", C.c_int), ("lat_w", C.c_int), ("channels", C.c_int), ("map_height", C.c_int),
+                ("map_width", C.c_int), ("ratio", C.c_float), ("key_capacity", C.c_int64), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_int64)]
+
+
 class srx_gbuffer_arrays(C.Structure):
     _fields_ = [("color", C.c_void_p), ("ids", C.c_void_p), ("pos", C.c_void_p), ("normal_depth", C.c_void_p),
                 ("noise", C.c_void_p), ("canny", C.c_void_p), ("canny_dtype", C.c_int)]
@@ -108,6 +117,7 @@ _PROTOTYPES = {
     "srx_plan_bind_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "srx_legacy_ordered_workspace_bytes": (C.c_int64, [C.POINTER(srx_legacy_desc)]),
     "srx_legacy_overlap_ordered": (C.c_int, [C.POINTER(srx_legacy_desc), C.POINTER(srx_legacy_args), C.c_int, C.c_void_p]),
+    "srx_johnny_overlap": (C.c_int, [C.POINTER(srx_legacy_desc), C.POINTER(srx_legacy_args), C.c_float, C.c_void_p, C.c_void_p]),
     "srx_corrmap_keys_workspace_bytes": (C.c_int64, [C.c_int64]),
     "srx_corrmap_first_appearance": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_int64, C.c_void_p]),
@@ -130,6 +140,10 @@ _PROTOTYPES = {
     "srx_plan_build_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "srx_plan_cache_entries": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]),
     "srx_plan_set_grid": (C.c_int, [C.c_void_p, C.c_int]),
+    "srx_plan_bind_multicast": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "srx_feature_overlap_workspace_bytes": (C.c_int64, [C.POINTER(srx_feature_args)]),
+    "srx_feature_overlap": (C.c_int, [C.POINTER(srx_feature_args), C.c_void_p]),
+    "srx_feature_overlap_check": (C.c_int, [C.POINTER(srx_feature_args), C.c_void_p]),
     "srx_plan_read_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "srx_plan_read_step_ring": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "srx_plan_destroy": (C.c_int, [C.c_void_p]),

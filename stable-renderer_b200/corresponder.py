@@ -96,6 +96,9 @@ class OverlapCorresponder:
     adain: bool = attrib(default=True, kw_only=True)
     process_group: Any = attrib(default=None, kw_only=True)
     exchange: str = attrib(default="auto", kw_only=True)
+    enable_post_attn_inject: bool = attrib(default=False, kw_only=True)
+    post_attn_map_size: Any = attrib(default=None, kw_only=True)
+    '''None = the reference's (IDMap.height, IDMap.width) = (W, 4) for [F,H,W,4] ids; or an explicit (height, width)'''
     cache_plan: bool = attrib(default=True, kw_only=True)
     '''bucket the ids once per id batch and run later denoise steps from the cached (key, cell) pairs'''
     '''frame-sharded multi-GPU runs (SURVEY.md §8e): when set, every rank reduces its own frames into the key-indexed
@@ -120,7 +123,16 @@ class OverlapCorresponder:
         return q_context, k_new, v_new
 
     def post_atten_inject(self, block, engine_data, origin_values: torch.Tensor, layer: int) -> torch.Tensor:
-        return origin_values   # dead in the reference as well (early return, corresponder.py:228)
+        """The reference returns `origin_values` before doing anything (corresponder.py:228) — the default here too.  With
+        `enable_post_attn_inject=True` the body behind that return (:230-295) runs on the GPU: the wide-channel feature
+        overlap of `feature.py` for layers above 10, blended with `post_attn_inject_ratio`."""
+        if not self.enable_post_attn_inject:
+            return origin_values
+        from .feature import POST_ATTN_SKIP_LAYERS, feature_overlap
+        if layer in POST_ATTN_SKIP_LAYERS:
+            return origin_values
+        return feature_overlap(origin_values, engine_data.id_maps, self.post_attn_inject_ratio,
+                               map_size=self.post_attn_map_size, key_capacity=int(self.key_capacity))
 
     # -- the hot path ----------------------------------------------------------------------------------------------
     def _plan(self, engine_data, id_map: IDMap, x: torch.Tensor) -> OverlapPlan:

@@ -71,7 +71,8 @@ struct FzParams {
     const int *fmap;
     char *ws;                 // this rank's workspace
     char *peers[SRX_MAX_PEERS];
-    long long ll_off;         // this rank's total records [ceil(kcap / world)] of 32 B (peer mode)
+    char *mc;                 // multicast (NVLS) view of the workspace: one address reaches every rank's copy; NULL = pull exchange
+    long long ll_off;         // total records of 32 B: this rank's slice [ceil(kcap / world)] (pull) or all kcap slots (NVLS)
     int ll_slice;             // slots per owner slice = ceil(kcap / world)
     long long accum_stride, pads_off, ctrl_off, stats_off;
     int *winner;
@@ -90,8 +91,7 @@ struct FzParams {
     int2 *pool;               // cached plan: (slot, cell << 6 | multiplicity - 1) entries, one region per CTA
     float *cnt_plan;          // cached plan: [kcap] entries per key on this rank (filled by EMIT; counts depend on the ids only)
     int dbg;                  // SRX_FZ_DEBUG experiment bits (results are wrong when set): 1 = no reductions,
-                              // 2 = consumers only drain the ring, 4 = stop after phase A, 8 = no count reductions,
-                              // 16 = no sum reductions
+                              // 2 = consumers only drain the ring, 4 = stop after phase A
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -227,6 +227,45 @@ __device__ __forceinline__ FzRec fz_rec_wait(const char *p, unsigned flag, int *
     return r;
 }
 
+// NVLS exchange (multimem.*: one instruction addresses the same offset on every rank through the NVSwitch).
+//   multimem.ld_reduce: the switch reads the addressed words on all ranks and returns their sum — the owner receives its
+//                       slice already reduced (1/world of the bytes a pull moves over its links);
+//   multimem.st:        one store lands in every rank's copy — the all-gather of the totals as a broadcast;
+//   multimem.red:       one arrival increments a counter on every rank.
+__device__ __forceinline__ float4 mm_ld_reduce_f4(const char *p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mm_st_f4(char *p, float a, float b, float c, float d) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mm_red_add_u32(char *p, unsigned v) {
+    asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Pushed total record (NVLS mode): two 16-byte halves {sum.x, sum.y, sum.z, step} {sum.w, count, step, 0}, each written by ONE
+// 16-byte multicast store, so each half carries its own flag; a reader takes the record once both flags show this step.
+__device__ __forceinline__ FzRec fz_rec2_wait(const char *p, unsigned flag, int *status) {
+    unsigned a, b, c, d, e, f, g, h;
+    unsigned spins = 0;
+    while (true) {
+        asm volatile("ld.relaxed.sys.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(f), "=r"(g), "=r"(h) : "l"(p) : "memory");
+        if (d == flag && g == flag) break;
+        __nanosleep(100);
+        if (++spins > FZ_SPIN_LIMIT || *reinterpret_cast<volatile int *>(status + FZ_ST_TIMEOUT)) {
+            atomicOr(status + FZ_ST_TIMEOUT, 1);
+            break;
+        }
+    }
+    FzRec r;
+    r.s = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(e));
+    r.c = __uint_as_float(f);
+    r.flag = d;
+    return r;
+}
+
 // 32-byte statistics record {3 doubles, step}: the 16 AdaIN partial sums of one CTA travel as six of them, each written
 // with ONE 256-bit store and polled with ONE 256-bit load, so a reader that sees this step's number also sees the data.
 // No atomics, no fence, no arrival counter; records never need clearing (step numbers only grow).
@@ -291,24 +330,26 @@ __device__ __forceinline__ void fz_barrier(const FzParams &P, int b, unsigned ta
 __device__ __forceinline__ int fz_slot_of(int v) {
     return ((unsigned)v >> 24) == 1u ? ((v + ((v >> 1) & 1)) & ~1) : v;
 }
-// Raw key of one pixel: its vertex id (float32-rounded when the table is large enough for that to matter) when the pixel
-// is an entry — map_index != 2048 and not an all-zero id, corrmap.py:266-275 — else -1.  The range check against the slot
-// table happens once per cell, on the warp-wide maximum.  (A vertex id of exactly -1 is therefore read as "no id".)
-__device__ __forceinline__ int fz_key_raw(int s, int m, int i, int v, bool big) {
+// key of one pixel: the dense slot of float32(vertexID), or -1 when the pixel is no entry (map_index == 2048 or an all-zero
+// id, corrmap.py:266-275)
+__device__ __forceinline__ int fz_key(int s, int m, int i, int v, unsigned kcap, int *status) {
     const bool valid = (i != SRX_NO_ID_MAP_INDEX) & ((s | m | i | v) != 0);
-    if (big) v = fz_slot_of(v);
-    return valid ? v : -1;
+    const int slot = fz_slot_of(v);
+    const bool inr = (unsigned)slot < kcap;
+    if (valid & !inr) atomicOr(status + FZ_ST_KEY_RANGE, 1);
+    return (valid & inr) ? slot : -1;
 }
-template <typename IdT> __device__ __forceinline__ void fz_keys_raw(uint32_t a, bool big, int &ka, int &kb);
-template <> __device__ __forceinline__ void fz_keys_raw<int4>(uint32_t a, bool big, int &ka, int &kb) {
+
+template <typename IdT> __device__ __forceinline__ void fz_keys(uint32_t a, unsigned kcap, int *status, int &ka, int &kb);
+template <> __device__ __forceinline__ void fz_keys<int4>(uint32_t a, unsigned kcap, int *status, int &ka, int &kb) {
     const int4 A = lds128(a), B = lds128(a + 16);
-    ka = fz_key_raw(A.x, A.y, A.z, A.w, big);
-    kb = fz_key_raw(B.x, B.y, B.z, B.w, big);
+    ka = fz_key(A.x, A.y, A.z, A.w, kcap, status);
+    kb = fz_key(B.x, B.y, B.z, B.w, kcap, status);
 }
-template <> __device__ __forceinline__ void fz_keys_raw<short4>(uint32_t a, bool big, int &ka, int &kb) {
+template <> __device__ __forceinline__ void fz_keys<short4>(uint32_t a, unsigned kcap, int *status, int &ka, int &kb) {
     const int4 v = lds128(a);
-    ka = fz_key_raw((int)(short)(v.x & 0xffff), v.x >> 16, (int)(short)(v.y & 0xffff), v.y >> 16, big);
-    kb = fz_key_raw((int)(short)(v.z & 0xffff), v.z >> 16, (int)(short)(v.w & 0xffff), v.w >> 16, big);
+    ka = fz_key((int)(short)(v.x & 0xffff), v.x >> 16, (int)(short)(v.y & 0xffff), v.y >> 16, kcap, status);
+    kb = fz_key((int)(short)(v.z & 0xffff), v.z >> 16, (int)(short)(v.w & 0xffff), v.w >> 16, kcap, status);
 }
 
 __device__ __forceinline__ double fz_warp_sum(double v) {
@@ -519,62 +560,77 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         unsigned ticket = 0, next_ticket = 0, in_batch = 0;
         unsigned k = 0;
         bool drawing = false;
-        while (true) {
-            unsigned item;
-            if (!drawing) {
-                item = blockIdx.x + k * G;
-                ++k;
-                if (k > per_cta || item >= static_end) {          // static share done
-                    if (!dynamic_tail) item = nitems;
-                    else {
+        auto next_item = [&]() -> unsigned {      // the deal described above; nitems = no more items
+            while (true) {
+                unsigned item = nitems;
+                if (!drawing) {
+                    item = blockIdx.x + k * G;
+                    ++k;
+                    if (k > per_cta || item >= static_end) {          // static share done
+                        if (!dynamic_tail) return nitems;
                         drawing = true;
                         if (lane == 0) ticket = atomicAdd(tickets, 1u) - tbase;
                         ticket = __shfl_sync(FULL, ticket, 0);
                         in_batch = 0;
                     }
                 }
-            }
-            if (drawing) {
-                if (in_batch == batch) { ticket = __shfl_sync(FULL, next_ticket, 0); in_batch = 0; }
-                item = ticket < nbatches ? static_end + ticket * batch + in_batch : nitems;
-                if (item < nitems && in_batch == 0 && lane == 0) next_ticket = atomicAdd(tickets, 1u) - tbase;   // hides behind this batch
-                if (item >= nitems && ticket < nbatches) {       // ragged last batch: fetch the (overdrawn) next ticket
-                    ticket = __shfl_sync(FULL, next_ticket, 0);
-                    in_batch = 0;
-                    continue;
+                if (drawing) {
+                    if (in_batch == batch) { ticket = __shfl_sync(FULL, next_ticket, 0); in_batch = 0; }
+                    item = ticket < nbatches ? static_end + ticket * batch + in_batch : nitems;
+                    if (item < nitems && in_batch == 0 && lane == 0) next_ticket = atomicAdd(tickets, 1u) - tbase;   // hides behind this batch
+                    if (item >= nitems && ticket < nbatches) {       // ragged last batch: fetch the (overdrawn) next ticket
+                        ticket = __shfl_sync(FULL, next_ticket, 0);
+                        in_batch = 0;
+                        continue;
+                    }
+                    ++in_batch;
                 }
-                ++in_batch;
+                return item;
             }
+        };
+        struct Item { int g, sy, fl, sx0, ncell; };
+        auto decode = [&](unsigned item) -> Item {
+            const int chunk = (int)item / P.nrows;
+            const int row = (int)item - chunk * P.nrows;
+            Item it;
+            it.g = row / P.h;
+            it.sy = row - it.g * P.h;
+            it.fl = __ldg(P.fmap + it.g);
+            it.sx0 = chunk * FZ_CELLS;
+            it.ncell = min(FZ_CELLS, P.w - it.sx0);
+            return it;
+        };
+        while (true) {
+            const unsigned cur = next_item();
             mbar_wait(sbase + L::BAR_OFF + (FZ_STAGES + stage) * 8, ph ^ 1u);
             const uint32_t sb = sbase + stage * L::STAGE;
             const uint32_t full = sbase + L::BAR_OFF + stage * 8;
-            if (item >= nitems) {                    // end marker for the consumers
+            if (cur >= nitems) {                     // end marker for the consumers
                 if (lane == 0) {
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb + L::DESC_OFF), "r"(0), "r"(-1), "r"(0), "r"(0) : "memory");
                     mbar_arrive(full);
                 }
                 break;
             }
-            const int chunk = (int)item / P.nrows;
-            const int row = (int)item - chunk * P.nrows;
-            const int g = row / P.h;
-            const int sy = row - g * P.h;
-            const int fl = __ldg(P.fmap + g);
-            const int sx0 = chunk * FZ_CELLS;
-            const int ncell = min(FZ_CELLS, P.w - sx0);
+            const Item it = decode(cur);
             if (lane == 0) {
-                // descriptor: first cell of the stage in the winner array, cells in the stage, element offset of the
-                // cells' channel-0 latents.  The latents themselves are fetched by the consumers with plain loads (eight
-                // scalars per warp): four more tiny bulk copies per stage cost 10 % of the streaming rate
-                // (tools/streamprobe, profiles/r2_streamprobe.txt)
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb + L::DESC_OFF), "r"((fl * P.h + sy) * P.w + sx0), "r"(ncell),
-                             "r"((fl * 4 * P.h + sy) * P.w + sx0), "r"(0) : "memory");
-                mbar_expect_tx(full, (uint32_t)(ncell * 64 * FzId<IdT>::PX));
+                // descriptor: first cell of the stage in the winner array, cells in the stage
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb + L::DESC_OFF), "r"((it.fl * P.h + it.sy) * P.w + it.sx0),
+                             "r"(it.ncell), "r"(0), "r"(0) : "memory");
+                mbar_expect_tx(full, (uint32_t)(it.ncell * (64 * FzId<IdT>::PX + (with_x ? 4 * (int)sizeof(XT) : 0))));
             }
             __syncwarp();
             if (lane < 8) {
-                const long long px = ((long long)g * P.H + sy * 8 + lane) * P.W + sx0 * 8;
-                bulk_g2s_hint(sb + lane * FzId<IdT>::PITCH, ids + px * FzId<IdT>::PX, (uint32_t)(ncell * 8 * FzId<IdT>::PX), full, pol);
+                const long long px = ((long long)it.g * P.H + it.sy * 8 + lane) * P.W + it.sx0 * 8;
+                bulk_g2s_hint(sb + lane * FzId<IdT>::PITCH, ids + px * FzId<IdT>::PX, (uint32_t)(it.ncell * 8 * FzId<IdT>::PX), full, pol);
+            } else if (lane < 12 && with_x) {
+                // The stage's latents ride on the same barrier as four small bulk copies.  They cost ~10 % of the pure
+                // streaming rate (tools/streamprobe), but every alternative that goes through the load/store unit — plain
+                // loads by the consumers at the start of a stage, one stage ahead, or by this warp one item ahead — queues
+                // behind the consumers' reductions and was measured slower (profiles/r2_latent_fetch_variants.txt).
+                const int ch = lane - 8;
+                bulk_g2s(sb + L::LAT_OFF + ch * FZ_CELLS * (int)sizeof(XT),
+                         x + ((long long)(it.fl * 4 + ch) * P.h + it.sy) * P.w + it.sx0, (uint32_t)(it.ncell * (int)sizeof(XT)), full);
             }
             if (++stage == FZ_STAGES) { stage = 0; ph ^= 1u; }
         }
@@ -593,128 +649,82 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         }
         const int r = lane >> 2, pr = lane & 3;
         const uint32_t lane_off = r * FzId<IdT>::PITCH + pr * 2 * FzId<IdT>::PX;
-        const bool big = P.kcap > (1u << 24);     // only then can a vertex id lose bits on its way through float32
-        const XT *xg = reinterpret_cast<const XT *>(P.x);
-        const int c0 = warp * FZ_CPW;             // this warp's first cell in every stage
-        const unsigned SLOT_MASK = (1u << FZ_SLOT_BITS) - 1u;
-        int bad = 0;
         int stage = 0;
         unsigned ph = 0;
         while (true) {
             mbar_wait(sbase + L::BAR_OFF + stage * 8, ph);
             const uint32_t sb = sbase + stage * L::STAGE;
-            const int4 desc = lds128(sb + L::DESC_OFF);
+            const int2 desc = lds64(sb + L::DESC_OFF);
             if (desc.y < 0) break;                    // end marker
-            // this warp's latents (FZ_CPW cells x 4 channels, lanes 0..7): requested now, used after the key work
-            float xl = 0.f;
-            if (with_x && lane < 4 * FZ_CPW && c0 + (lane >> 2) < desc.y)
-                xl = XIo<XT>::ld(xg + desc.z + (long long)(lane & 3) * n + c0 + (lane >> 2));
             int ka[FZ_CPW], kb[FZ_CPW];
+            float xv[FZ_CPW][4];
 #pragma unroll
             for (int u = 0; u < FZ_CPW; ++u) {
-                fz_keys_raw<IdT>(sb + lane_off + (c0 + u) * 8 * FzId<IdT>::PX, big, ka[u], kb[u]);
-                if (c0 + u >= desc.y) ka[u] = kb[u] = -1;   // warp-uniform (ragged last chunk of a row: stale bytes there)
+                const int cell = warp * FZ_CPW + u;
+                ka[u] = kb[u] = -1;
+                if (cell < desc.y)   // warp-uniform (ragged last chunk of a row: the stage holds stale bytes there)
+                    fz_keys<IdT>(sb + lane_off + cell * 8 * FzId<IdT>::PX, P.kcap, P.status, ka[u], kb[u]);
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) xv[u][ch] = lds_x<XT>(sb + L::LAT_OFF + ch * FZ_CELLS * (int)sizeof(XT), cell);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(sbase + L::BAR_OFF + (FZ_STAGES + stage) * 8);   // stage may be refilled
             if (++stage == FZ_STAGES) { stage = 0; ph ^= 1u; }
             if (P.dbg & 2) continue;
 
-            // Everything below runs on the warp's FZ_CPW cells side by side, without branches in the common case, so that
-            // the REDUX / shuffle latencies of one cell hide behind the other's (four warps per scheduler cannot hide them).
-            // Keys are raw vertex ids here (-1 = no entry); one warp-wide maximum per cell range-checks all 64 pixels.
-            unsigned um[FZ_CPW];                      // 1 + the cell's largest key, 0 = no entry in the cell
 #pragma unroll
-            for (int u = 0; u < FZ_CPW; ++u) um[u] = __reduce_max_sync(FULL, max((unsigned)ka[u] + 1u, (unsigned)kb[u] + 1u));
-            {
-                unsigned worst = um[0];
-#pragma unroll
-                for (int u = 1; u < FZ_CPW; ++u) worst = max(worst, um[u]);
-                if (worst > P.kcap) {                 // rare: a vertex id outside the slot table — drop those pixels, flag the plan
-                    bad = 1;
-#pragma unroll
-                    for (int u = 0; u < FZ_CPW; ++u) {
-                        if ((unsigned)ka[u] >= P.kcap) ka[u] = -1;
-                        if ((unsigned)kb[u] >= P.kcap) kb[u] = -1;
-                        um[u] = __reduce_max_sync(FULL, max((unsigned)ka[u] + 1u, (unsigned)kb[u] + 1u));
+            for (int u = 0; u < FZ_CPW; ++u) {
+                const int cell = warp * FZ_CPW + u;
+                if (cell >= desc.y) break;            // warp-uniform
+                const int a = ka[u], b = kb[u];
+                const int hi = __reduce_max_sync(FULL, max(a, b));
+                if (hi < 0) {                         // no entry in this cell
+                    if (lane == 0) P.winner[desc.x + cell] = -1;
+                    continue;
+                }
+                // winner = last valid pixel in row-major order: positions 2*lane (a) and 2*lane+1 (b), stored +1
+                unsigned wp = 0;
+                if (b >= 0) wp = ((unsigned)(2 * lane + 2) << FZ_SLOT_BITS) | (unsigned)b;
+                else if (a >= 0) wp = ((unsigned)(2 * lane + 1) << FZ_SLOT_BITS) | (unsigned)a;
+                wp = __reduce_max_sync(FULL, wp);
+                if (lane == 0) P.winner[desc.x + cell] = (int)(wp & ((1u << FZ_SLOT_BITS) - 1u));
+                const unsigned lo = __reduce_min_sync(FULL, min((unsigned)a, (unsigned)b));
+                if (P.dbg & 1) continue;
+                // reduce-by-key inside the warp -> up to two (key, multiplicity) pairs per lane:
+                //   * one key in the whole cell (REDUX min == max): a single pair for the cell;
+                //   * otherwise the lane's two horizontally adjacent pixels merge when equal, and vertically adjacent rows
+                //     (lane L = row 2i, lane L+4 = row 2i+1, same columns) merge pairwise through two shuffles.  Magnified
+                //     textures (several pixels per texel) are where this pays: every merge saves two L2 atomics.
+                int k1 = a, k2 = (a == b) ? -1 : b, m1 = (a == b) ? 2 : 1, m2 = 1;
+                if ((int)lo == hi) {
+                    const int total = __reduce_add_sync(FULL, (a >= 0) + (b >= 0));
+                    k1 = lane == 0 ? hi : -1;
+                    k2 = -1;
+                    m1 = total;
+                } else {
+                    const bool upper = (lane & 4) == 0;                       // even row of the cell
+                    const int o1 = __shfl_xor_sync(FULL, k1, 4), o2 = __shfl_xor_sync(FULL, k2, 4);
+                    const int om1 = __shfl_xor_sync(FULL, m1, 4);
+                    // first slots: same column pair, rows 2i / 2i+1.  Equal keys: the upper lane takes both.
+                    if (k1 >= 0 && o1 == k1) {
+                        if (upper) m1 += om1; else k1 = -1;
+                    }
+                    if (k2 >= 0 && o2 == k2) {                                // second slots (multiplicity 1 on both sides)
+                        if (upper) m2 += 1; else k2 = -1;
                     }
                 }
-            }
-            unsigned lo[FZ_CPW], wp[FZ_CPW];
-#pragma unroll
-            for (int u = 0; u < FZ_CPW; ++u) {
-                lo[u] = __reduce_min_sync(FULL, min((unsigned)ka[u], (unsigned)kb[u]));
-                // winner = last valid pixel in row-major order: positions 2*lane (a) and 2*lane+1 (b), stored +1
-                unsigned w = 0;
-                if (kb[u] >= 0) w = ((unsigned)(2 * lane + 2) << FZ_SLOT_BITS) | (unsigned)kb[u];
-                else if (ka[u] >= 0) w = ((unsigned)(2 * lane + 1) << FZ_SLOT_BITS) | (unsigned)ka[u];
-                wp[u] = __reduce_max_sync(FULL, w);
-            }
-            if (lane < FZ_CPW && c0 + lane < desc.y) {   // lane u stores cell u's winner: one store instruction per stage
-                unsigned w = wp[0], m = um[0];
-#pragma unroll
-                for (int u = 1; u < FZ_CPW; ++u) if (lane == u) { w = wp[u]; m = um[u]; }
-                P.winner[desc.x + c0 + lane] = m ? (int)(w & SLOT_MASK) : -1;
-            }
-            if (P.dbg & 1) continue;
-            {
-                unsigned any = um[0];
-#pragma unroll
-                for (int u = 1; u < FZ_CPW; ++u) any |= um[u];
-                if (any == 0) continue;               // no entry in any of the cells (warp-uniform): outside every object
-            }
-            // reduce-by-key inside the warp -> up to two (key, multiplicity) pairs per lane and cell:
-            //   * the lane's two horizontally adjacent pixels merge when equal, and vertically adjacent rows (lane L = row 2i,
-            //     lane L+4 = row 2i+1, same columns) merge pairwise through shuffles.  Magnified textures (several pixels per
-            //     texel) are where this pays: every merge saves two L2 atomics;
-            //   * one key in the whole cell (min == max): a single pair for the cell.
-            int k1[FZ_CPW], k2[FZ_CPW], m1[FZ_CPW], m2[FZ_CPW];
-            const bool upper = (lane & 4) == 0;       // even row of the cell
-#pragma unroll
-            for (int u = 0; u < FZ_CPW; ++u) {
-                const bool same = ka[u] == kb[u];
-                k1[u] = ka[u];
-                k2[u] = same ? -1 : kb[u];
-                m1[u] = same ? 2 : 1;
-                m2[u] = 1;
-            }
-#pragma unroll
-            for (int u = 0; u < FZ_CPW; ++u) {
-                const int o1 = __shfl_xor_sync(FULL, k1[u], 4), o2 = __shfl_xor_sync(FULL, k2[u], 4);
-                const int om1 = __shfl_xor_sync(FULL, m1[u], 4);
-                // first slots: same column pair, rows 2i / 2i+1.  Equal keys: the upper lane takes both.
-                if (k1[u] >= 0 && o1 == k1[u]) {
-                    if (upper) m1[u] += om1; else k1[u] = -1;
-                }
-                if (k2[u] >= 0 && o2 == k2[u]) {      // second slots (multiplicity 1 on both sides)
-                    if (upper) m2[u] += 1; else k2[u] = -1;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < FZ_CPW; ++u) {
-                if (um[u] != 0 && lo[u] + 1u == um[u]) {          // warp-uniform: one key in the whole cell
-                    const int total = __reduce_add_sync(FULL, (ka[u] >= 0) + (kb[u] >= 0));
-                    k1[u] = lane == 0 ? (int)lo[u] : -1;
-                    k2[u] = -1;
-                    m1[u] = total;
-                }
-            }
-            if (P.mode != FZ_MODE_STEP) {
-                // bucketing passes: the pairs are counted / stored instead of reduced
-#pragma unroll
-                for (int u = 0; u < FZ_CPW; ++u) {
-                    if (um[u] == 0) continue;         // warp-uniform
-                    const int cell = c0 + u;
+                if (P.mode != FZ_MODE_STEP) {
+                    // bucketing passes: the pairs are counted / stored instead of reduced
                     if (P.mode == FZ_MODE_MARK) {
-                        const int w = (int)(wp[u] & SLOT_MASK);
-                        const int np = __popc(__ballot_sync(FULL, k1[u] >= 0)) + __popc(__ballot_sync(FULL, k2[u] >= 0));
+                        const int w = (int)(wp & ((1u << FZ_SLOT_BITS) - 1u));
+                        const int np = __popc(__ballot_sync(FULL, k1 >= 0)) + __popc(__ballot_sync(FULL, k2 >= 0));
                         if (lane == 0) {
                             P.need[w] = 1;
                             atomicAdd(s_fill, (unsigned)np);
                         }
                     } else {   // EMIT
-                        const bool fa = k1[u] >= 0 && __ldg(P.need + k1[u]) != 0;
-                        const bool fb = k2[u] >= 0 && __ldg(P.need + k2[u]) != 0;
+                        const bool fa = k1 >= 0 && __ldg(P.need + k1) != 0;
+                        const bool fb = k2 >= 0 && __ldg(P.need + k2) != 0;
                         const unsigned ba = __ballot_sync(FULL, fa), bb = __ballot_sync(FULL, fb);
                         const int tot = __popc(ba) + __popc(bb);
                         unsigned base = 0;
@@ -724,34 +734,28 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
                         const unsigned cellg = (unsigned)(desc.x + cell) << 6;
                         int2 *dst = P.pool + P.cta_tab[2 * gridDim.x + blockIdx.x] + base;
                         if (fa) {
-                            dst[__popc(ba & lt)] = make_int2(k1[u], (int)(cellg | (unsigned)(m1[u] - 1)));
-                            red_add_f32(P.cnt_plan + k1[u], (float)m1[u]);
+                            dst[__popc(ba & lt)] = make_int2(k1, (int)(cellg | (unsigned)(m1 - 1)));
+                            red_add_f32(P.cnt_plan + k1, (float)m1);
                         }
                         if (fb) {
-                            dst[__popc(ba) + __popc(bb & lt)] = make_int2(k2[u], (int)(cellg | (unsigned)(m2[u] - 1)));
-                            red_add_f32(P.cnt_plan + k2[u], (float)m2[u]);
+                            dst[__popc(ba) + __popc(bb & lt)] = make_int2(k2, (int)(cellg | (unsigned)(m2 - 1)));
+                            red_add_f32(P.cnt_plan + k2, (float)m2);
                         }
                     }
+                    continue;
                 }
-                continue;
-            }
-#pragma unroll
-            for (int u = 0; u < FZ_CPW; ++u) {
-                const float x0 = __shfl_sync(FULL, xl, 4 * u), x1 = __shfl_sync(FULL, xl, 4 * u + 1),
-                            x2 = __shfl_sync(FULL, xl, 4 * u + 2), x3 = __shfl_sync(FULL, xl, 4 * u + 3);
-                if (k1[u] >= 0) {
-                    const float fm = (float)m1[u];
-                    if (!(P.dbg & 16)) red_add_f32x4(acc + (long long)k1[u] * 4, fm * x0, fm * x1, fm * x2, fm * x3);
-                    if (!(P.dbg & 8)) red_add_f32(cnt + k1[u], fm);
+                if (k1 >= 0) {
+                    const float fm = (float)m1;
+                    red_add_f32x4(acc + (long long)k1 * 4, fm * xv[u][0], fm * xv[u][1], fm * xv[u][2], fm * xv[u][3]);
+                    red_add_f32(cnt + k1, fm);
                 }
-                if (k2[u] >= 0) {
-                    const float fm = (float)m2[u];
-                    if (!(P.dbg & 16)) red_add_f32x4(acc + (long long)k2[u] * 4, fm * x0, fm * x1, fm * x2, fm * x3);
-                    if (!(P.dbg & 8)) red_add_f32(cnt + k2[u], fm);
+                if (k2 >= 0) {
+                    const float fm = (float)m2;
+                    red_add_f32x4(acc + (long long)k2 * 4, fm * xv[u][0], fm * xv[u][1], fm * xv[u][2], fm * xv[u][3]);
+                    red_add_f32(cnt + k2, fm);
                 }
             }
         }
-        if (bad) atomicOr(P.status + FZ_ST_KEY_RANGE, 1);
     }
 
     if (P.mode == FZ_MODE_MARK || P.mode == FZ_MODE_EMIT) {   // bucketing passes end here; the step counter does not move
@@ -787,7 +791,36 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
     // tools/nvl_probe.py.
     const bool xchg = P.world > 1;
     const int slice = P.ll_slice;
-    if (xchg) {
+    if (xchg && P.mc) {
+        // NVLS form.  Owner side: the switch reduces this rank's slice over all ranks (multimem.ld_reduce), the totals go
+        // out to every rank as flagged records (multimem.st) — no pull of world-1 partial slices, no signal round, and
+        // phase B below polls LOCAL records instead of fetching them from their owners.
+        const int gthreads = gridDim.x * FZ_THREADS;
+        const char *mca = P.mc + (long long)par * P.accum_stride;
+        char *mct = P.mc + P.ll_off;
+        for (int base = blockIdx.x * FZ_THREADS + (tid - lane); base < slice; base += gthreads) {
+            const int i = base + lane;
+            const long long k = (long long)P.rank * slice + i;
+            const bool live = i < slice && k < (long long)P.kcap;     // uniform over every aligned group of 4 lanes
+            float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), cv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) sv = mm_ld_reduce_f4(mca + k * 16);
+            if (live && (lane & 3) == 0) cv = mm_ld_reduce_f4(mca + (long long)P.kcap * 16 + k * 4);   // counts of slots k..k+3
+            const int src = lane & ~3;
+            const float c0 = __shfl_sync(FULL, cv.x, src), c1 = __shfl_sync(FULL, cv.y, src), c2 = __shfl_sync(FULL, cv.z, src),
+                        c3 = __shfl_sync(FULL, cv.w, src);
+            const float c = (lane & 2) ? ((lane & 1) ? c3 : c2) : ((lane & 1) ? c1 : c0);
+            if (live && c > 0.f) {                    // slots nobody contributed to are never looked up
+                mm_st_f4(mct + k * 32, sv.x, sv.y, sv.z, __uint_as_float(epoch));
+                mm_st_f4(mct + k * 32 + 16, sv.w, c, __uint_as_float(epoch), 0.f);
+            }
+        }
+        FZ_TRACE(3);
+        // this CTA no longer reads any rank's accumulator of this step (they are cleared two steps on): one multicast
+        // arrival tells every rank
+        __syncthreads();
+        if (tid == 0) mm_red_add_u32(P.mc + P.pads_off + (1 * SRX_MAX_PEERS + P.rank) * 4, 1u);
+        FZ_TRACE(4);
+    } else if (xchg) {
         const int gtid = blockIdx.x * FZ_THREADS + tid, gthreads = gridDim.x * FZ_THREADS;
         const long long aoff = (long long)par * P.accum_stride;
         if (P.world <= 4) fz_pull_slice<2, 4>(P, acc, aoff, slice, epoch, gtid, gthreads);
@@ -852,24 +885,18 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         double sums[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) sums[j] = 0.0;
-        int slot_next[FZ_BU];
-#pragma unroll
-        for (int u = 0; u < FZ_BU; ++u) {
-            const int ci = s0 + tid + u * FZ_THREADS;
-            slot_next[u] = ci < s1 ? __ldcg(wf + ci) : -2;
-        }
         for (int c0 = s0 + tid; c0 < s1; c0 += FZ_BU * FZ_THREADS) {
-            // FZ_BU cells per thread per round, loads grouped by dependency level (winner -> accumulator), and the winners
-            // of the NEXT round requested before this round's accumulator loads: one L2 round trip per round
+            // FZ_BU cells per thread per round, loads grouped by dependency level (winner -> accumulator) so that a
+            // round costs two L2 round trips instead of 2 * FZ_BU  (requesting the next round's winners a round ahead was
+            // measured slower: 21 instead of 17.5 us on cfg3)
             int slot[FZ_BU];
             float xv[FZ_BU][4];
             float4 a[FZ_BU];
             float cn[FZ_BU];
 #pragma unroll
             for (int u = 0; u < FZ_BU; ++u) {
-                slot[u] = slot_next[u];
-                const int cn_i = c0 + (FZ_BU + u) * FZ_THREADS;
-                slot_next[u] = cn_i < s1 ? __ldcg(wf + cn_i) : -2;
+                const int ci = c0 + u * FZ_THREADS;
+                slot[u] = ci < s1 ? __ldcg(wf + ci) : -2;
             }
 #pragma unroll
             for (int u = 0; u < FZ_BU; ++u) {
@@ -889,7 +916,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
                 a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 cn[u] = 1.f;
                 if (slot[u] >= 0) {
-                    if (xchg) {                       // the owner's record of this step (remote for foreign slots)
+                    if (xchg && P.mc) {               // NVLS: the owner pushed this step's total into every rank's table
+                        const FzRec r = fz_rec2_wait(P.ws + P.ll_off + (long long)slot[u] * 32, epoch, P.status);
+                        a[u] = r.s;
+                        cn[u] = r.c;
+                    } else if (xchg) {                // the owner's record of this step (remote for foreign slots)
                         const int o = slot[u] / slice;
                         const FzRec r = fz_rec_wait(P.peers[o] + P.ll_off + (long long)(slot[u] - o * slice) * 32, epoch, P.status);
                         a[u] = r.s;
@@ -1093,7 +1124,8 @@ static int launch_fused_t(srx_plan *p, const srx_step_args *a, cudaStream_t st, 
     for (int i = 0; i < SRX_MAX_PEERS; ++i) P.peers[i] = p->world > 1 ? p->peers[i] : nullptr;
     P.peers[p->world > 1 ? p->rank : 0] = p->ws;
     P.ll_off = p->ll_off;
-    P.ll_slice = (int)((p->kcap + p->world - 1) / p->world);
+    P.mc = (p->world > 1 && p->mc && p->kcap % 4 == 0 && p->ll_bytes >= p->kcap * 32) ? p->mc : nullptr;
+    P.ll_slice = (int)(((p->kcap + p->world - 1) / p->world + 3) / 4 * 4);   // multiple of 4: count vectors never straddle owners
     P.accum_stride = p->accum_stride;
     P.pads_off = p->pads_off;
     P.ctrl_off = p->ctrl_off;
@@ -1242,6 +1274,18 @@ extern "C" int srx_plan_bind_peers(srx_plan *p, int rank, int world, void *const
     }
     p->world = world;
     p->rank = rank;
+    return SRX_OK;
+}
+
+// NVLS: `mc_ws` is the multicast address of the (symmetric) workspace — the same offset on every rank behind one pointer
+// (torch symmetric memory: multicast_ptr).  Call after srx_plan_bind_peers, on every rank or on none; NULL switches back to
+// the pull exchange.
+extern "C" int srx_plan_bind_multicast(srx_plan *p, void *mc_ws) {
+    SRX_REQUIRE(p && p->ws, SRX_ERR_INVALID, "bind the local workspace first");
+    SRX_REQUIRE(!mc_ws || p->world > 1, SRX_ERR_INVALID, "bind the peers first (srx_plan_bind_peers)");
+    SRX_REQUIRE(!mc_ws || (p->kcap % 4 == 0 && p->ll_bytes >= p->kcap * 32), SRX_ERR_UNSUPPORTED,
+                "the NVLS exchange needs a key capacity that is a multiple of 4 and at most 4 Mi slots");
+    p->mc = reinterpret_cast<char *>(mc_ws);
     return SRX_OK;
 }
 

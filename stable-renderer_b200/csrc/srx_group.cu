@@ -236,55 +236,88 @@ __device__ __forceinline__ int gr_pixel_rank(const IdT *ids, long long px, const
     return table[vertex_slot(p.v)];
 }
 
-// 'nearest': F.interpolate(size = (H/8, W/8)) keeps source pixel (8i, 8j)   (loaders.py:252-255)
+// Which entry ends up in full-resolution pixel (Y, X) of latent frame f?  The node writes `latent[frame, :, sy, sx] = row`
+// for every entry with sx = trunc(fl32(x / H) * S), sy = trunc(fl32(y / W) * S) (loaders.py:218-219 with corrmap.py:239,249);
+// duplicates resolve to the LAST entry in (id frame, y, x) order.  With an id map of the working size the candidates are the
+// pixel (Y, X) itself; a larger map sends several pixels to one target, a smaller one leaves holes (the base draw stays);
+// several id frames may write one latent frame (the chain inv_frame[f] -> prev_frame[g] -> ..., latest first).
+struct NoiseGeom {
+    int F, H, W, S;
+    const int *inv_frame, *prev_frame;
+};
+__device__ __forceinline__ int gr_axis_map(int p, int div, int S) { return (int)__fmul_rn(__fdiv_rn((float)p, (float)div), (float)S); }
+// pixels p in [0, n) with gr_axis_map(p, div, S) == T form one run [lo, hi] (the map is monotone); hi < lo = none
+__device__ __forceinline__ void gr_axis_range(int T, int n, int div, int S, int &lo, int &hi) {
+    int p = (int)(((long long)T * div) / S) - 2;
+    if (p < 0) p = 0;
+    while (p < n && gr_axis_map(p, div, S) < T) ++p;
+    lo = p;
+    while (p < n && gr_axis_map(p, div, S) == T) ++p;
+    hi = p - 1;
+}
 template <typename IdT>
-__global__ void __launch_bounds__(GR_THREADS) k_noise_nearest(const IdT *__restrict__ ids, const int *__restrict__ inv_frame,
+__device__ __forceinline__ int gr_target_rank(const IdT *ids, const NoiseGeom &g, const int *__restrict__ table, int f, int Y, int X) {
+    int ylo = Y, yhi = Y, xlo = X, xhi = X;
+    if (g.H != g.S || g.W != g.S) {
+        gr_axis_range(Y, g.H, g.W, g.S, ylo, yhi);      // y / width
+        gr_axis_range(X, g.W, g.H, g.S, xlo, xhi);      // x / height
+        if (yhi < ylo || xhi < xlo) return -1;
+    }
+    for (int gi = g.inv_frame[f]; gi >= 0; gi = g.prev_frame ? g.prev_frame[gi] : -1) {
+        for (int y = yhi; y >= ylo; --y)
+            for (int x = xhi; x >= xlo; --x) {
+                const int r = gr_pixel_rank(ids, ((long long)gi * g.H + y) * g.W + x, table);
+                if (r >= 0) return r;
+            }
+    }
+    return -1;
+}
+
+// 'nearest': F.interpolate(size = (S/8, S/8)) keeps source pixel (8i, 8j)   (loaders.py:252-255)
+template <typename IdT>
+__global__ void __launch_bounds__(GR_THREADS) k_noise_nearest(const IdT *__restrict__ ids, NoiseGeom g,
                                                                const int *__restrict__ table, const float *__restrict__ key_a,
                                                                const float *__restrict__ key_b, const float *__restrict__ base_a,
                                                                const float *__restrict__ base_b, float *__restrict__ out_a,
-                                                               float *__restrict__ out_b, int F, int H, int W) {
-    const int h = H / 8, w = W / 8;
-    const long long total = (long long)F * h * w;
+                                                               float *__restrict__ out_b) {
+    const int S = g.S, h = S / 8, w = S / 8;
+    const long long total = (long long)g.F * h * w;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(t % w);
         const int i = (int)((t / w) % h);
         const int f = (int)(t / ((long long)w * h));
-        const int g = inv_frame[f];
-        const long long src = (long long)(8 * i) * W + 8 * j;
-        int r = -1;
-        if (g >= 0) r = gr_pixel_rank(ids, (long long)g * H * W + src, table);
+        const long long src = (long long)(8 * i) * S + 8 * j;
+        const int r = gr_target_rank(ids, g, table, f, 8 * i, 8 * j);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const long long o = (((long long)f * 4 + c) * h + i) * w + j;
-            out_a[o] = r >= 0 ? key_a[(long long)r * 4 + c] : base_a[(long long)c * H * W + src];
-            out_b[o] = r >= 0 ? key_b[(long long)r * 4 + c] : base_b[(long long)c * H * W + src];
+            out_a[o] = r >= 0 ? key_a[(long long)r * 4 + c] : base_a[(long long)c * S * S + src];
+            out_b[o] = r >= 0 ? key_b[(long long)r * 4 + c] : base_b[(long long)c * S * S + src];
         }
     }
 }
 
 // 'mean' / 'max' / 'min': the node views the full-resolution tensor as [-1, 4, 8, 8] — 256 CONSECUTIVE floats of a row,
 // not an 8x8 block — and reduces dims (1, 2): out[chunk, k] = op over a < 4, b < 8 of row[chunk*256 + a*64 + b*8 + k]
-// (loaders.py:257-268).  The result holds F*4*H*W/32 floats, which the node then views as [-1, 4, H/8, W/8] (2F frames).
+// (loaders.py:257-268).  The result holds F*4*S*S/32 floats, which the node then views as [-1, 4, S/8, S/8] (2F frames).
 template <typename IdT>
-__global__ void __launch_bounds__(GR_THREADS) k_noise_pool(const IdT *__restrict__ ids, const int *__restrict__ inv_frame,
+__global__ void __launch_bounds__(GR_THREADS) k_noise_pool(const IdT *__restrict__ ids, NoiseGeom g,
                                                             const int *__restrict__ table, const float *__restrict__ key_b,
-                                                            const float *__restrict__ base_b, float *__restrict__ out_b,
-                                                            int F, int H, int W, int op) {
-    const long long total = (long long)F * 4 * H * W / 32;
+                                                            const float *__restrict__ base_b, float *__restrict__ out_b, int op) {
+    const int S = g.S;
+    const long long total = (long long)g.F * 4 * S * S / 32;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(t & 7);
-        const long long first = (t >> 3) * 256;            // flat index of the chunk's first float in [F,4,H,W]
-        const int x0 = (int)(first % W);
-        const int y = (int)((first / W) % H);
-        const int c = (int)((first / ((long long)W * H)) % 4);
-        const int f = (int)(first / ((long long)W * H * 4));
-        const int g = inv_frame[f];
+        const long long first = (t >> 3) * 256;            // flat index of the chunk's first float in [F,4,S,S]
+        const int x0 = (int)(first % S);
+        const int y = (int)((first / S) % S);
+        const int c = (int)((first / ((long long)S * S)) % 4);
+        const int f = (int)(first / ((long long)S * S * 4));
         float acc = op == 1 ? 0.f : (op == 2 ? -INFINITY : INFINITY);
         for (int ab = 0; ab < 32; ++ab) {
             const int x = x0 + ab * 8 + k;
-            int r = -1;
-            if (g >= 0) r = gr_pixel_rank(ids, ((long long)g * H + y) * W + x, table);
-            const float v = r >= 0 ? key_b[(long long)r * 4 + c] : base_b[((long long)c * H + y) * W + x];
+            const int r = gr_target_rank(ids, g, table, f, y, x);
+            const float v = r >= 0 ? key_b[(long long)r * 4 + c] : base_b[((long long)c * S + y) * S + x];
             acc = op == 1 ? acc + v : (op == 2 ? fmaxf(acc, v) : fminf(acc, v));
         }
         out_b[t] = op == 1 ? acc / 32.f : acc;
@@ -295,28 +328,30 @@ extern "C" int srx_noise_from_ids(const srx_noise_args *a, void *stream) {
     SRX_REQUIRE(a && a->ids_dev && a->inv_frame_dev && a->rank_table_dev && a->key_noise_dev && a->base_noise_dev && a->noise_out_dev,
                 SRX_ERR_INVALID, "null argument");
     SRX_REQUIRE(a->id_dtype == SRX_I32 || a->id_dtype == SRX_I16, SRX_ERR_INVALID, "id dtype must be int32 or int16");
-    SRX_REQUIRE(a->frames > 0 && a->height > 0 && a->width > 0 && a->height % 8 == 0 && a->width % 256 == 0, SRX_ERR_INVALID,
-                "height must be a multiple of 8 and width a multiple of 256");
+    const int S = a->work_size > 0 ? a->work_size : a->height;
+    SRX_REQUIRE(a->frames > 0 && a->height > 0 && a->width > 0, SRX_ERR_INVALID, "non-positive dimension");
+    SRX_REQUIRE(S % 256 == 0, SRX_ERR_INVALID, "the working size must be a multiple of 256 (the node uses 512 / 1024)");
+    SRX_REQUIRE(a->work_size > 0 || a->height == a->width, SRX_ERR_INVALID, "work_size == 0 means a square id map of the working size");
     SRX_REQUIRE(a->mode >= 0 && a->mode <= 3, SRX_ERR_INVALID, "mode must be 0 nearest, 1 mean, 2 max, 3 min");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int F = a->frames, H = a->height, W = a->width;
+    NoiseGeom g{a->frames, a->height, a->width, S, a->inv_frame_dev, a->prev_frame_dev};
     if (a->mode == 0) {
         SRX_REQUIRE(a->key_latent_dev && a->base_latent_dev && a->latent_out_dev, SRX_ERR_INVALID, "nearest mode needs the latent tensors too");
-        const long long total = (long long)F * (H / 8) * (W / 8);
+        const long long total = (long long)g.F * (S / 8) * (S / 8);
         if (a->id_dtype == SRX_I32)
-            k_noise_nearest<int4><<<gr_grid(total), GR_THREADS, 0, st>>>(reinterpret_cast<const int4 *>(a->ids_dev), a->inv_frame_dev, a->rank_table_dev,
-                a->key_latent_dev, a->key_noise_dev, a->base_latent_dev, a->base_noise_dev, a->latent_out_dev, a->noise_out_dev, F, H, W);
+            k_noise_nearest<int4><<<gr_grid(total), GR_THREADS, 0, st>>>(reinterpret_cast<const int4 *>(a->ids_dev), g, a->rank_table_dev,
+                a->key_latent_dev, a->key_noise_dev, a->base_latent_dev, a->base_noise_dev, a->latent_out_dev, a->noise_out_dev);
         else
-            k_noise_nearest<short4><<<gr_grid(total), GR_THREADS, 0, st>>>(reinterpret_cast<const short4 *>(a->ids_dev), a->inv_frame_dev, a->rank_table_dev,
-                a->key_latent_dev, a->key_noise_dev, a->base_latent_dev, a->base_noise_dev, a->latent_out_dev, a->noise_out_dev, F, H, W);
+            k_noise_nearest<short4><<<gr_grid(total), GR_THREADS, 0, st>>>(reinterpret_cast<const short4 *>(a->ids_dev), g, a->rank_table_dev,
+                a->key_latent_dev, a->key_noise_dev, a->base_latent_dev, a->base_noise_dev, a->latent_out_dev, a->noise_out_dev);
     } else {
-        const long long total = (long long)F * 4 * H * W / 32;
+        const long long total = (long long)g.F * 4 * S * S / 32;
         if (a->id_dtype == SRX_I32)
-            k_noise_pool<int4><<<gr_grid(total), GR_THREADS, 0, st>>>(reinterpret_cast<const int4 *>(a->ids_dev), a->inv_frame_dev, a->rank_table_dev,
-                a->key_noise_dev, a->base_noise_dev, a->noise_out_dev, F, H, W, a->mode);
+            k_noise_pool<int4><<<gr_grid(total), GR_THREADS, 0, st>>>(reinterpret_cast<const int4 *>(a->ids_dev), g, a->rank_table_dev,
+                a->key_noise_dev, a->base_noise_dev, a->noise_out_dev, a->mode);
         else
-            k_noise_pool<short4><<<gr_grid(total), GR_THREADS, 0, st>>>(reinterpret_cast<const short4 *>(a->ids_dev), a->inv_frame_dev, a->rank_table_dev,
-                a->key_noise_dev, a->base_noise_dev, a->noise_out_dev, F, H, W, a->mode);
+            k_noise_pool<short4><<<gr_grid(total), GR_THREADS, 0, st>>>(reinterpret_cast<const short4 *>(a->ids_dev), g, a->rank_table_dev,
+                a->key_noise_dev, a->base_noise_dev, a->noise_out_dev, a->mode);
     }
     SRX_CUDA_CHECK(cudaGetLastError());
     return SRX_OK;

@@ -22,6 +22,7 @@ struct srx_plan {
     int64_t accum_stride = 0, pads_off = 0, ctrl_off = 0, stats_off = 0, stats_bytes = 0, ll_off = 0, ll_bytes = 0;
     int world = 1, rank = 0;
     char *peers[SRX_MAX_PEERS] = {nullptr};
+    char *mc = nullptr;   // multicast (NVLS) address of the workspace, NULL = pull exchange
     int fused_grid = 0;   // CTAs of the persistent kernel; 0 = one per SM
     // cached plan (srx_plan_build_cache)
     int64_t need_off = 0, ctatab_off = 0, cntp_off = 0, cache_entries_cap = -1;
@@ -51,9 +52,11 @@ static inline void plan_layout(srx_plan *p) {
     off += 256;
     p->ctrl_off = off;   // [0] step counter; +64 phase stamps of the first / last CTA; +256 ring of per-step (first CTA
     off += 4096;         // start, last CTA end) global-timer stamps; +1024 ring of the first CTA's phase stamps (profiling aids)
-    // peer mode: this rank's slice of exchanged totals, [ceil(K / world)] records of 32 B {sum.xyzw, count, step}; world >= 2
+    // peer mode: exchanged totals as 32-byte records.  Pull exchange: this rank's slice, [ceil(K / world)] records
+    // {sum.xyzw, count, step}, world >= 2.  NVLS exchange: all K records (every owner broadcasts its slice); tables of more
+    // than 4 Mi slots keep the half-size region and the pull exchange.
     p->ll_off = off;
-    p->ll_bytes = p->fused ? (p->kcap / 2 + 64) * 32 : 0;
+    p->ll_bytes = p->fused ? (p->kcap <= (4ll << 20) ? p->kcap + 64 : p->kcap / 2 + 64) * 32 : 0;
     off = align_up(off + p->ll_bytes, 256);
     p->winner_off = off;
     p->winner_bytes = (int64_t)d.batch * d.lat_h * d.lat_w * 4;

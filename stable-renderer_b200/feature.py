@@ -1,0 +1,64 @@
+"""Wide-channel feature overlap: the body of `OverlapCorresponder.post_atten_inject`
+(reference source/common_utils/stable_render_utils/corresponder.py:236-295 — unreachable there behind an early return) on the
+GPU: `[B, h*w, c]` post-attention features, same-key features averaged across frames and blended back, AdaIN of the original
+features to the result's statistics.  One sort-based bucketing pass per call (`csrc/srx_feature.cu`)."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .corrmap import IDMap
+
+POST_ATTN_SKIP_LAYERS = tuple(range(11))     # corresponder.py:232-234: "post atten inject does not seem effective" there
+
+
+def feature_overlap(origin_values: torch.Tensor, id_map: IDMap, ratio: float = 0.6,
+                    map_size: Optional[Tuple[int, int]] = None, key_capacity: int = 0, check: bool = True) -> torch.Tensor:
+    """origin_values [B, h*w, c] (h*w a perfect square) -> new tensor of the same shape and dtype.
+
+    map_size: the (height, width) the features are up-sampled to before the per-pixel gather.  The reference passes
+              `(id_map.height, id_map.width)`, which for `[F,H,W,4]` ids are `(W, 4)` (corrmap.py:85-93) — the default here,
+              to stay a drop-in; `(H, W)` is what the comment in the reference intends ("match the size of the id map").
+    key_capacity: exclusive upper bound of the vertex ids; 0 = one `max()` over the ids (syncs)."""
+    if not origin_values.is_cuda:
+        raise _lib.SrxUnavailable("features must live on a CUDA device (there is no CPU path)")
+    if origin_values.dim() != 3:
+        raise ValueError(f"features must be [B, h*w, c], got {tuple(origin_values.shape)}")
+    B, hw, c = (int(v) for v in origin_values.shape)
+    h = int(round(math.sqrt(hw)))
+    if h * h != hw:
+        raise ValueError(f"Dimension hw={hw} is not a perfect square.")
+    dev = origin_values.device
+    ids = id_map.device_ids(dev)
+    F, H, W = int(ids.shape[0]), int(ids.shape[1]), int(ids.shape[2])
+    mh, mw = (int(id_map.height), int(id_map.width)) if map_size is None else (int(map_size[0]), int(map_size[1]))
+    if key_capacity <= 0:
+        key_capacity = int(ids[..., 3].max().item()) + 1
+    feat = origin_values.contiguous()
+    out = torch.empty_like(feat)
+    fmap = torch.tensor([int(v) for v in id_map.frame_indices], dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    a = _lib.srx_feature_args()
+    a.ids_dev, a.id_dtype, a.frames, a.height, a.width = ids.data_ptr(), _lib.torch_dtype_code(ids.dtype), F, H, W
+    a.frame_map_dev = fmap.data_ptr()
+    a.feat_dev, a.out_dev, a.x_dtype = feat.data_ptr(), out.data_ptr(), _lib.torch_dtype_code(feat.dtype)
+    a.batch, a.lat_h, a.lat_w, a.channels = B, h, h, c
+    a.map_height, a.map_width, a.ratio, a.key_capacity = mh, mw, float(ratio), int(key_capacity)
+    nbytes = int(lib.srx_feature_overlap_workspace_bytes(C.byref(a)))
+    if nbytes < 0:
+        _lib.check(_lib.SRX_ERR_INVALID if c * feat.element_size() % 16 == 0 and c <= 1280 else _lib.SRX_ERR_UNSUPPORTED)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    with torch.cuda.device(dev):
+        stream = _lib.current_stream_ptr(dev)
+        _lib.check(lib.srx_feature_overlap(C.byref(a), stream))
+        if check:
+            _lib.check(lib.srx_feature_overlap_check(C.byref(a), stream))
+    return out
+
+
+__all__ = ["feature_overlap", "POST_ATTN_SKIP_LAYERS"]

@@ -44,17 +44,19 @@ class CreateNoiseSequenceFromIdMap:
         ids = ids.contiguous()
         F, H, W = int(ids.shape[0]), int(ids.shape[1]), int(ids.shape[2])
         size = _SIZES[sd_version]
-        if H != size or W != size:
-            # the reference scales pixel coordinates by size / H (loaders.py:218-219); only the 1:1 case is built here
-            raise _lib.SrxError(f"id maps of {H}x{W} with sd_version={sd_version} ({size}x{size}) are not supported")
+        if H != W:
+            # x is divided by the height and y by the width (corrmap.py:239,249): a non-square map indexes out of the latent
+            raise IndexError(f"id maps must be square, got {H}x{W}")
+        # An id map of another size than the node's working size: entry (x, y) lands in pixel (trunc(fl32(x/H)*size),
+        # trunc(fl32(y/W)*size)) (loaders.py:218-219) — several pixels per target when the map is larger (the last one in entry
+        # order wins), holes when it is smaller (the base draw stays).  The kernels invert that mapping per target pixel.
         frame_values = [int(v) for v in id_map.frame_indices]
-        inv = [-1] * F
+        inv, prev = [-1] * F, [-1] * F
         for g, v in enumerate(frame_values):
             if v < -F or v >= F:
                 raise IndexError(f"index {v} is out of bounds for dimension 0 with size {F}")
-            inv[v % F] = g                      # several id frames on one latent frame: the last one wins, as index_put does
-        if len(set(v % F for v in frame_values)) != len(frame_values):
-            raise _lib.SrxError("several id frames map to one latent frame: not supported")
+            prev[g] = inv[v % F]                # several id frames on one latent frame: entries are written in id-frame order,
+            inv[v % F] = g                      # so the latest id frame with an entry at the target wins (as index_put does)
         dev = ids.device
         lib = _lib.load()
 
@@ -84,12 +86,14 @@ class CreateNoiseSequenceFromIdMap:
                 noise = torch.empty(F, 4, h, w, dtype=torch.float32, device=dev)
             else:
                 latent = None
-                noise = torch.empty(F * 4 * size * size // 32, dtype=torch.float32, device=dev)
+                noise = torch.empty(F * 4 * size * size // 32, dtype=torch.float32, device=dev)   # [F,4,S,S] viewed as [-1,4,8,8]
             a = _lib.srx_noise_args()
             a.ids_dev, a.id_dtype = ids.data_ptr(), _lib.torch_dtype_code(ids.dtype)
             a.frames, a.height, a.width = F, H, W
             inv_t = torch.tensor(inv, dtype=torch.int32, device=dev)
+            prev_t = torch.tensor(prev, dtype=torch.int32, device=dev)
             a.inv_frame_dev, a.rank_table_dev = inv_t.data_ptr(), table.data_ptr()
+            a.work_size, a.prev_frame_dev = size, prev_t.data_ptr()
             a.key_latent_dev, a.key_noise_dev = key_latent.data_ptr(), key_noise.data_ptr()
             a.base_latent_dev, a.base_noise_dev = base_latent.data_ptr(), base_noise.data_ptr()
             a.latent_out_dev = latent.data_ptr() if latent is not None else None

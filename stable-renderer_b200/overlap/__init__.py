@@ -4,10 +4,11 @@ from .algorithms import (AverageDistance, FrameDistance, OverlapAlgorithm, Perpe
                          overlap_algorithm_factory)
 from .correspondence import CorrespondenceMap
 from .driver import Overlap, ResizeOverlap
+from . import johnny as johnny_overlap
 from .latent import CorrMapLatentNoiseInitializer
 from .scheduler import Scheduler, value_interpolation
 from .view_normal import build_view_normal_map
 
 __all__ = ["OverlapAlgorithm", "AverageDistance", "FrameDistance", "PixelDistance", "PerpendicularViewNormal",
            "overlap_algorithm_factory", "CorrespondenceMap", "Overlap", "ResizeOverlap", "Scheduler",
-           "value_interpolation", "build_view_normal_map", "CorrMapLatentNoiseInitializer"]
+           "value_interpolation", "build_view_normal_map", "CorrMapLatentNoiseInitializer", "johnny_overlap"]

@@ -120,9 +120,25 @@ class ResizeOverlap(Overlap):
         if alpha == 0:
             return frame_seq                                    # overlap.py:200-201
         if self._interpolate_mode != "nearest":
-            raise NotImplementedError("only interpolate_mode='nearest' (the reference default) is supported")
+            return self._call_interpolated(frame_seq, corr_map, step, timestep, **kwargs)
         alpha, radius = self._schedule(step, timestep)
         stack = torch.stack(frame_seq, dim=0).contiguous()      # [T,B,C,h,w]
         T, B, Cc, h, w = stack.shape
         self._run(stack.view(T, B * Cc, h, w), corr_map, alpha, kwargs.get("view_normal_map"), radius)
         return list(stack.unbind(0))
+
+
+    def _call_interpolated(self, frame_seq, corr_map, step, timestep, **kwargs) -> List[torch.Tensor]:
+        """interpolate_mode != 'nearest' (overlap.py:205-221): the latents are really resampled — up to the map size with
+        `F.interpolate`, overlapped there at full resolution (the same kernels with latent size = map size), resampled back, and
+        merged with `torch.where(ovlp != 0, ovlp, original)`.  The nearest mode never builds the 64x larger tensors; the smooth
+        modes have no such shortcut, every map pixel carries its own interpolated value."""
+        import torch.nn.functional as F
+        mode = self._interpolate_mode
+        align_corners = False if mode in ("linear", "bilinear", "bicubic", "trilinear") else None
+        screen_w, screen_h = corr_map.size
+        frame_h, frame_w = frame_seq[0].shape[-2:]
+        up = [F.interpolate(latents, size=(screen_h, screen_w), mode=mode, align_corners=align_corners) for latents in frame_seq]
+        stack = Overlap.__call__(self, up, corr_map, step=step, timestep=timestep, **kwargs)
+        down = [F.interpolate(latents, size=(frame_h, frame_w), mode=mode, align_corners=align_corners) for latents in stack]
+        return [torch.where(down[i] != 0, down[i], frame_seq[i]) for i in range(len(frame_seq))]

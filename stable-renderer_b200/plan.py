@@ -65,6 +65,8 @@ class OverlapPlan:
             info = _lib.srx_plan_info()
             _lib.check(lib.srx_plan_get_info(self._handle, C.byref(info)))
             self.info = info
+            self.key_capacity_hint = int(info.key_capacity)
+            self.nvls = False
             self.fused = bool(info.fused)
             self.group = process_group
             self.world = 1
@@ -75,6 +77,9 @@ class OverlapPlan:
                 import torch.distributed as dist
                 self.world = dist.get_world_size(process_group)
                 self.exchange = "nccl"
+            self._want_nvls = exchange == "nvls" or bool(os.environ.get("SRX_NVLS"))
+            if exchange == "nvls":
+                exchange = "peer"
             want_peer = self.world > 1 and exchange in ("auto", "peer")
             if exchange == "peer" and self.world > 1 and not self.fused:
                 raise _lib.SrxError("exchange='peer' needs the persistent step kernel (8x8 pixels per cell, 4 channels, "
@@ -122,6 +127,26 @@ class OverlapPlan:
         dist.barrier(group=self.group)               # ... on every rank before anyone signals a peer
         _lib.check(lib.srx_plan_bind_peers(self._handle, rank, self.world, arr))
         self.exchange = "peer"
+        # NVLS (opt-in: SRX_NVLS=1, or exchange="nvls"): when the symmetric allocation has a multicast mapping on EVERY rank,
+        # the in-kernel exchange reduces inside the NVSwitch (multimem.ld_reduce) and broadcasts the totals (multimem.st)
+        # instead of pulling world-1 slices.  Measured on 8 x B200 (profiles/r2_exchange_nvls_vs_pull.txt) it is correct but
+        # not faster than the pull exchange (N=8: 105 vs 101 us per cfg3 step; N=4: 166 vs 145; N=2: 247 vs 236): the
+        # in-switch reduction returns after ~9 us and the broadcast of all non-empty slots moves more bytes than the pull
+        # of the needed records — so the pull form stays the default.
+        self.nvls = False
+        mc = 0
+        if self._want_nvls and not os.environ.get("SRX_NO_NVLS"):
+            try:
+                mc = int(self._symm.multicast_ptr or 0)
+            except Exception:  # noqa: BLE001 - no multicast support in this torch build / on this fabric
+                mc = 0
+            if self.key_capacity_hint % 4 != 0 or self.key_capacity_hint > (4 << 20):
+                mc = 0
+        ok = torch.tensor([1 if mc else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            _lib.check(lib.srx_plan_bind_multicast(self._handle, C.c_void_p(mc)))
+            self.nvls = True
 
     def bind_peers(self, rank: int, peer_workspaces: Sequence[int]) -> None:
         """Low-level peer binding from raw workspace device pointers (tests emulate two ranks on one GPU with it)."""

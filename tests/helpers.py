@@ -58,3 +58,40 @@ def scripted_ksampler(*args, callbacks=(), **kwargs):
             cb(ctx)
         x = ctx.noise * 0.8 + ctx.denoised * 0.2
     return ({"samples": x},)
+
+
+def torch_chain(ids: torch.Tensor, x: torch.Tensor, ratio: float) -> torch.Tensor:
+    """The reference's op chain (corresponder.py:298-376) in torch ops with float64 sums and an explicit last writer per cell: the
+    referee of the full-size GPU tests (any device; pinned to the reference fixtures on the CPU)."""
+    F, H, W, _ = ids.shape
+    B, C, h, w = x.shape
+    x64 = x.double()
+    K = int(ids[..., 3].max().item()) + 1
+    sums = torch.zeros(K, C, dtype=torch.float64, device=x.device)
+    cnts = torch.zeros(K, dtype=torch.float64, device=x.device)
+    winner = torch.full((B * h * w,), -1, dtype=torch.int64, device=x.device)     # packed (pixel order, key) of the last valid pixel
+    for f in range(F):
+        idf = ids[f]
+        keep = (idf[..., 2] != 2048) & (idf != 0).any(dim=-1)                     # corrmap.py:266-275
+        yy, xx = keep.nonzero(as_tuple=True)
+        key = idf[yy, xx, 3].to(torch.float32).long()                              # the key goes through float32 (corrmap.py:256-261)
+        sx = ((xx.float() / H) * w).long()                                         # corresponder.py:312-313 with corrmap.py:239,249
+        sy = ((yy.float() / W) * h).long()
+        cell = (f * h + sy) * w + sx
+        vals = x64[f][:, sy, sx].t()                                               # [n, C]
+        sums.index_add_(0, key, vals)
+        cnts.index_add_(0, key, torch.ones_like(key, dtype=torch.float64))
+        order = yy * W + xx                                                        # entry order inside the frame
+        winner.scatter_reduce_(0, cell, order * K + key, reduce="amax")
+    mean = (sums / cnts.clamp(min=1).unsqueeze(1)).float()                         # reference sums and divides in float32
+    has = winner >= 0
+    wkey = (winner % K).clamp(min=0)
+    flat = x.float().permute(0, 2, 3, 1).reshape(-1, C)                            # [B*h*w, C]
+    blended = torch.where(has.unsqueeze(1), (1 - ratio) * flat + ratio * mean[wkey], flat)
+    b = blended.reshape(B, h, w, C).permute(0, 3, 1, 2).reshape(B, C, -1).double()
+    c = x64.reshape(B, C, -1)
+    c_mean, c_std = c.mean(2, keepdim=True), (c.var(2, keepdim=True) + 1e-5).sqrt()
+    s_mean, s_std = b.mean(2, keepdim=True), (b.var(2, keepdim=True) + 1e-5).sqrt()
+    return ((c - c_mean) / c_std * s_std + s_mean).reshape(B, C, h, w)
+
+

@@ -61,7 +61,7 @@ def main():
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"max abs err rank0 {err.max():.3e}; exchange={plan.exchange}", flush=True)
+        print(f"max abs err rank0 {err.max():.3e}; exchange={plan.exchange} nvls={getattr(plan, 'nvls', False)}", flush=True)
         print("PEER_OK" if int(flag.item()) == 1 else "PEER_MISMATCH", flush=True)
     dist.barrier()
     dist.destroy_process_group()

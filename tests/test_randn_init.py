@@ -110,3 +110,31 @@ def test_gpu_noise_sequence_permuted_frames_vs_oracle():
     vsi = O.vertex_screen_info(ids.numpy(), fi)
     k0 = vsi[(vsi[:, 4] * size).astype(int) % 8 == 0]
     assert k0.size > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["map_1024_on_sd15", "map_256_on_sd15", "map_384_on_sd15", "two_id_frames_one_latent_frame"])
+def test_gpu_noise_sequence_other_map_sizes_and_shared_frames_vs_oracle(case):
+    """Id maps that are not the node's working size (several pixels per target pixel: the last entry wins; fewer: holes keep the
+    base draw; a non-integer ratio), and several id frames writing one latent frame (loaders.py:218-243)."""
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import IDMap
+    from stable_renderer_b200.loaders import CreateNoiseSequenceFromIdMap
+    size, seed = 512, 321
+    H, fi = {"map_1024_on_sd15": (1024, [0, 1]), "map_256_on_sd15": (256, [1, 0]), "map_384_on_sd15": (384, [0, 1]),
+             "two_id_frames_one_latent_frame": (512, [0, 0, 2])}[case]
+    F = len(fi)
+    ids = synthetic.make_ids(F, H, H, tex_h=150, tex_w=150, frac_2048=0.1, seed=9)
+    n_unique = len(np.unique(O.vertex_screen_info(ids.numpy(), fi)[:, 3]))
+    bl, bn, kl, kn = _node_draws(seed, size, n_unique)
+    idm = IDMap(tensor=ids.cuda(), frame_indices=fi)
+    for option in ("nearest", "max", "mean"):
+        want_s, want_n = O.noise_sequence_from_ids(ids.numpy(), fi, bl, bn, kl, kn, size, option)
+        out = CreateNoiseSequenceFromIdMap()(idm, seed, "SD15", option, rng_device="cpu")
+        if option == "mean":
+            np.testing.assert_allclose(out["noise"].cpu().numpy(), want_n, rtol=1e-6, atol=1e-7)
+        else:
+            assert np.array_equal(out["noise"].cpu().numpy(), want_n), (case, option)
+            assert np.array_equal(out["samples"].cpu().numpy(), want_s), (case, option)
+    with pytest.raises(IndexError):
+        CreateNoiseSequenceFromIdMap()(IDMap(tensor=torch.zeros(1, 64, 128, 4, dtype=torch.int32).cuda()), 1)

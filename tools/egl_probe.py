@@ -16,10 +16,16 @@ for path in ("/usr/lib/x86_64-linux-gnu/libEGL.so.1", "/usr/lib/x86_64-linux-gnu
     print(f"{path}: {'present' if os.path.exists(path) else 'absent'}")
 os.system("ls /usr/lib/x86_64-linux-gnu | grep -i -E 'egl|libgl|mesa|glvnd' | head -20; ls /usr/share/glvnd/egl_vendor.d 2>/dev/null")
 
-try:
-    egl = C.CDLL("libEGL.so.1")
-except OSError as e:
-    print(f"libEGL.so.1 cannot be loaded: {e}\nRESULT: no GL context possible on this box; cudaGraphicsGLRegisterImage cannot be exercised")
+egl = None
+for cand in ("libEGL.so.1", "libEGL_nvidia.so.0"):      # the glvnd dispatcher, else the driver's vendor library directly
+    try:
+        egl = C.CDLL(cand)
+        print(f"loaded {cand}")
+        break
+    except OSError as e:
+        print(f"{cand} cannot be loaded: {e}")
+if egl is None or not hasattr(egl, "eglGetProcAddress"):
+    print("RESULT: no GL context possible on this box; cudaGraphicsGLRegisterImage cannot be exercised")
     sys.exit(0)
 
 EGL_PLATFORM_DEVICE_EXT, EGL_NONE, EGL_OPENGL_API = 0x313F, 0x3038, 0x30A2
@@ -65,11 +71,28 @@ for i in range(n.value):
 if not ctx_ok:
     print("RESULT: EGL present but no OpenGL context could be made current; cudaGraphicsGLRegisterImage cannot be exercised")
     sys.exit(0)
-gl = C.CDLL("libGL.so.1") if os.path.exists("/usr/lib/x86_64-linux-gnu/libGL.so.1") else C.CDLL("libOpenGL.so.0")
+def glfn(name, restype, *argtypes):
+    addr = egl.eglGetProcAddress(name.encode())
+    if not addr:
+        raise RuntimeError(f"{name} not found")
+    return C.CFUNCTYPE(restype, *argtypes)(addr)
+
+
+try:
+    glGenTextures = glfn("glGenTextures", None, C.c_int, C.POINTER(C.c_uint))
+    glBindTexture = glfn("glBindTexture", None, C.c_uint, C.c_uint)
+    glTexStorage2D = glfn("glTexStorage2D", None, C.c_uint, C.c_int, C.c_uint, C.c_int, C.c_int)
+    glGetError = glfn("glGetError", C.c_uint)
+    glFinish = glfn("glFinish", None)
+except RuntimeError as e:
+    print(f"RESULT: context current but GL entry points missing: {e}")
+    sys.exit(0)
 tex = C.c_uint(0)
-gl.glGenTextures(1, C.byref(tex))
-gl.glBindTexture(0x0DE1, tex)
-gl.glTexStorage2D(0x0DE1, 1, 0x881A, 64, 32)              # GL_RGBA16F
+glGenTextures(1, C.byref(tex))
+glBindTexture(0x0DE1, tex.value)
+glTexStorage2D(0x0DE1, 1, 0x881A, 64, 32)              # GL_RGBA16F
+glFinish()
+print(f"GL texture {tex.value} created, glGetError = {glGetError()}")
 import torch  # noqa: E402
 from stable_renderer_b200.texture import Texture  # noqa: E402
 t = Texture(64, 32, 4, torch.float16, gl_texture=tex.value)

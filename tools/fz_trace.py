@@ -21,6 +21,8 @@ torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 frames_cfg, H, h, dtype, tex, n_obj, scaling = WORKLOADS[wl]
+if os.environ.get('SRX_TRACE_FRAMES'):
+    frames_cfg = int(os.environ['SRX_TRACE_FRAMES'])
 F, f0, F_global = shard(frames_cfg, scaling, rank, world)
 dev = torch.device("cuda", local)
 ids = [synthetic.make_ids(F, H, H, tex_h=tex, tex_w=tex, n_obj=n_obj, frac_2048=0.05, seed=1234, device=dev, frame_offset=f0)]
