@@ -241,10 +241,12 @@ typedef struct srx_legacy_args {
     const float *view_normal_dev; /* [T,H,W] float32 for SRX_STRATEGY_VIEW_NORMAL (utils.py:56-102), else NULL */
     void *workspace_dev;       /* srx_legacy_workspace_bytes() bytes */
     int64_t workspace_bytes;
+    int defer_status;          /* 1 = no host sync inside srx_legacy_overlap: sticky status, reported by srx_legacy_check */
 } srx_legacy_args;
 int64_t srx_legacy_workspace_bytes(const srx_legacy_desc *desc);
 /* Errors (after a sync) with SRX_ERR_KEY_RANGE when an id component does not fit the packed 64-bit key. */
 int srx_legacy_overlap(const srx_legacy_desc *desc, const srx_legacy_args *args, void *stream);
+int srx_legacy_check(const srx_legacy_desc *desc, const srx_legacy_args *args, void *stream);
 
 /* kernel_radius > 0 (overlap.py:61-80,137-145): the reference pools the diagonal neighbours (y+d, x+d), d in [-r, r], and
  * writes every blended trace into the storage it keeps reading, trace after trace in dict order — a Gauss-Seidel sweep whose
@@ -323,12 +325,16 @@ typedef struct srx_bake_args {
                                   3 = copy the claimed texels into the atlas.  Workspace: srx_bake_sharded_workspace_bytes(). */
     int frame_offset;          /* view-sharded reference modes: index of this rank's first view among all ranks' views */
     int frames_global;         /* ... and the number of views of all ranks together (frames_global * H * W < 2^31) */
+    int defer_status;          /* 1 = no host sync inside the call: the status word stays sticky in the (initially zeroed)
+                                  workspace until srx_bake_check reads it — graph-capturable, like srx_plan_check for the step */
 } srx_bake_args;
 int64_t srx_bake_workspace_bytes(int k2, int texels, int channels, int weight_mode);
 /* [owner words k2*texels*4, 256-aligned][256 status][partial atlas k2*texels*channels*2, 256-aligned] */
 int64_t srx_bake_sharded_workspace_bytes(int k2, int texels, int channels);
 /* Errors with SRX_ERR_INDEX (after a sync) when a kept pixel addresses a texel outside the atlas. */
 int srx_bake_update(const srx_bake_args *args, void *stream);
+/* Deferred form (args->defer_status): reports and clears the status of the calls since the last check.  Syncs. */
+int srx_bake_check(const srx_bake_args *args, void *stream);
 
 /* On-disk atlas format — the arithmetic of CorrespondMap.dump / Load (source/engine/static/corrmap.py:776-791, 846-858):
  * uint8 = clip(255 * value, 0, 255) evaluated in float16 like numpy does, flags 0 / 255; and back: float32(u8) / 255 stored

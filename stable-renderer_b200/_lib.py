@@ -55,7 +55,8 @@ class srx_legacy_desc(C.Structure):
 
 class srx_legacy_args(C.Structure):
     _fields_ = [("x_dev", C.c_void_p), ("x_dtype", C.c_int), ("ids_dev", C.c_void_p), ("alpha", C.c_float),
-                ("view_normal_dev", C.c_void_p), ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("view_normal_dev", C.c_void_p), ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_int64),
+                ("defer_status", C.c_int)]
 
 
 class srx_noise_args(C.Structure):
@@ -73,7 +74,7 @@ class srx_bake_args(C.Structure):
                 ("frames", C.c_int), ("height", C.c_int), ("width", C.c_int), ("sprite_id", C.c_int),
                 ("material_id", C.c_int), ("ignore_obj_mat_id", C.c_int), ("mode", C.c_int), ("weight_mode", C.c_int),
                 ("normal_depth_dev", C.c_void_p), ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_int64), ("phase", C.c_int),
-                ("frame_offset", C.c_int), ("frames_global", C.c_int)]
+                ("frame_offset", C.c_int), ("frames_global", C.c_int), ("defer_status", C.c_int)]
 
 
 class srx_gbuffer(C.Structure):
@@ -157,8 +158,10 @@ _PROTOTYPES = {
                                             C.c_int64, C.c_void_p]),
     "srx_legacy_workspace_bytes": (C.c_int64, [C.POINTER(srx_legacy_desc)]),
     "srx_legacy_overlap": (C.c_int, [C.POINTER(srx_legacy_desc), C.POINTER(srx_legacy_args), C.c_void_p]),
+    "srx_legacy_check": (C.c_int, [C.POINTER(srx_legacy_desc), C.POINTER(srx_legacy_args), C.c_void_p]),
     "srx_bake_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "srx_bake_update": (C.c_int, [C.POINTER(srx_bake_args), C.c_void_p]),
+    "srx_bake_check": (C.c_int, [C.POINTER(srx_bake_args), C.c_void_p]),
     "srx_gl_register_image": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint, C.c_uint, C.c_uint]),
     "srx_gl_map": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     "srx_gl_unmap": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -261,8 +261,12 @@ class CorrespondMap:
     def update(self, color_frames, id_maps, spriteID: int | None = None, materialID: int | None = None,
                mode: UpdateMode = "first_avg", masks=None, inverse_masks: bool = False, ignore_obj_mat_id: bool = False,
                weight_mode: BakeWeight = "none", normal_depth: Optional[Tensor] = None, process_group=None,
-               phase: int = 0, frame_offset: int = 0, frames_global: int = 0):
+               phase: int = 0, frame_offset: int = 0, frames_global: int = 0, defer_check: bool = False):
         """`CorrespondMap.update` (reference corrmap.py:578-670): same arguments; all frames go to the GPU in one call.
+
+        defer_check: by default a pixel that addresses a texel outside the atlas raises IndexError from this call, as in the
+        reference — which costs one host sync per call.  With `defer_check=True` the call only enqueues its kernels (no host
+        sync, CUDA-graph capturable); the status stays on the device until `check()` raises for everything since the last check.
 
         weight_mode / normal_depth select the depth/normal-weighted multi-view bake, which the
         reference lists as TODO (README.md:18-19); "none" is the reference behaviour.
@@ -323,8 +327,10 @@ class CorrespondMap:
         if wm == 0 and (sharded or phase):
             need = int(lib.srx_bake_sharded_workspace_bytes(self.k * self.k, self.height * self.width, self.channel_count))
         if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._workspace = torch.zeros(need, dtype=torch.uint8, device=self.device)    # zeroed: the deferred status word is sticky
         a = _lib.srx_bake_args()
+        a.defer_status = 1 if defer_check else 0
+        self._last_args = a
         a.values_dev = self._values.data_ptr()
         a.writtens_dev = self._writtens.data_ptr()
         a.k2, a.texels, a.channels = self.k * self.k, self.height * self.width, self.channel_count
@@ -373,6 +379,15 @@ class CorrespondMap:
             else:
                 a.phase = int(phase)
                 _lib.check(lib.srx_bake_update(C.byref(a), stream))
+
+    def check(self) -> None:
+        """Raises IndexError if an `update(..., defer_check=True)` since the last check addressed a texel outside the atlas
+        (syncs the current stream)."""
+        a = getattr(self, "_last_args", None)
+        if a is None:
+            return
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().srx_bake_check(C.byref(a), _lib.current_stream_ptr(self.device)))
 
     @staticmethod
     def _stack(frames, what: str) -> Tensor:

@@ -353,7 +353,7 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
     if (a->weight_mode == SRX_WEIGHT_NONE) {
         unsigned int *owner = reinterpret_cast<unsigned int *>(ws);
         status = reinterpret_cast<int *>(ws + bk_align(ntex * 4));
-        if (a->phase <= 1) SRX_CUDA_CHECK(cudaMemsetAsync(status, 0, 256, st));
+        if (a->phase <= 1 && !a->defer_status) SRX_CUDA_CHECK(cudaMemsetAsync(status, 0, 256, st));
         if (a->phase != 0) {
             // view-sharded bake of the reference modes: order keys number the views of ALL ranks, the owner words are
             // MAX-reduced between phase 1 and 2, the ranks' partial atlases SUM-reduced (as int32 words) between phase 2 and 3
@@ -387,7 +387,7 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
                 k_bake_merge<<<gridt, 256, 0, st>>>(owner, delta, values, a->writtens_dev, ntex, g.C);
             }
             SRX_CUDA_CHECK(cudaGetLastError());
-            if (a->phase != 1) return SRX_OK;      // the status word is written by the claim pass only
+            if (a->phase != 1 || a->defer_status) return SRX_OK;      // the status word is written by the claim pass only
             int st_claim = 0;
             SRX_CUDA_CHECK(cudaMemcpyAsync(&st_claim, status, sizeof(int), cudaMemcpyDeviceToHost, st));
             SRX_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -432,7 +432,8 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
         float *wsum = reinterpret_cast<float *>(ws + bk_align(ntex * 16));
         status = reinterpret_cast<int *>(ws + bk_align(ntex * 16) + bk_align(ntex * 4));
         if (a->phase != 2) {
-            SRX_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)(bk_align(ntex * 16) + bk_align(ntex * 4) + 256), st));
+            // (deferred status: the status block stays as it is — sticky until srx_bake_check reads and clears it)
+            SRX_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)(bk_align(ntex * 16) + bk_align(ntex * 4) + (a->defer_status ? 0 : 256)), st));
             g.frames_total = a->frames;
             const long long npx = (long long)a->frames * hw;
             long long nb = (npx + 255) / 256;
@@ -459,6 +460,7 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
         }
     }
     SRX_CUDA_CHECK(cudaGetLastError());
+    if (a->defer_status) return SRX_OK;           // no host sync: srx_bake_check reports (and clears) the status later
     int st_host = 0;
     SRX_CUDA_CHECK(cudaMemcpyAsync(&st_host, status, sizeof(int), cudaMemcpyDeviceToHost, st));
     SRX_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -496,6 +498,25 @@ extern "C" int srx_bake_update(const srx_bake_args *a, void *stream) {
     if (a->id_dtype == SRX_I32) return bake_color_dispatch<int4>(a, st);
     if (a->id_dtype == SRX_I16) return bake_color_dispatch<short4>(a, st);
     return srx_set_error(SRX_ERR_INVALID, "id dtype must be int32 or int16");
+}
+
+// Deferred status (args->defer_status = 1): srx_bake_update enqueues its kernels and returns without touching the host; the
+// status word in the workspace stays sticky across such calls (the workspace must start zeroed) until this call reads it,
+// clears it and reports SRX_ERR_INDEX if any of them addressed a texel outside the atlas.  Syncs the stream.
+extern "C" int srx_bake_check(const srx_bake_args *a, void *stream) {
+    SRX_REQUIRE(a && a->workspace_dev, SRX_ERR_INVALID, "null argument");
+    const long long ntex = (long long)a->k2 * a->texels;
+    char *ws = reinterpret_cast<char *>(a->workspace_dev);
+    int *status = reinterpret_cast<int *>(a->weight_mode == SRX_WEIGHT_NONE ? ws + bk_align(ntex * 4) : ws + bk_align(ntex * 16) + bk_align(ntex * 4));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int st_host = 0;
+    SRX_CUDA_CHECK(cudaMemcpyAsync(&st_host, status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SRX_CUDA_CHECK(cudaMemsetAsync(status, 0, 256, st));
+    SRX_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (st_host)
+        return srx_set_error(SRX_ERR_INDEX, "index out of range: a kept pixel addresses (map_index, vertexID) outside the "
+                             "%d x %d atlas (corrmap.py:735)", a->k2, a->texels);
+    return SRX_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

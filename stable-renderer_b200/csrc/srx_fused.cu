@@ -560,77 +560,61 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_overlap_fused(const __grid_co
         unsigned ticket = 0, next_ticket = 0, in_batch = 0;
         unsigned k = 0;
         bool drawing = false;
-        auto next_item = [&]() -> unsigned {      // the deal described above; nitems = no more items
-            while (true) {
-                unsigned item = nitems;
-                if (!drawing) {
-                    item = blockIdx.x + k * G;
-                    ++k;
-                    if (k > per_cta || item >= static_end) {          // static share done
-                        if (!dynamic_tail) return nitems;
+        while (true) {
+            unsigned item;
+            if (!drawing) {
+                item = blockIdx.x + k * G;
+                ++k;
+                if (k > per_cta || item >= static_end) {          // static share done
+                    if (!dynamic_tail) item = nitems;
+                    else {
                         drawing = true;
                         if (lane == 0) ticket = atomicAdd(tickets, 1u) - tbase;
                         ticket = __shfl_sync(FULL, ticket, 0);
                         in_batch = 0;
                     }
                 }
-                if (drawing) {
-                    if (in_batch == batch) { ticket = __shfl_sync(FULL, next_ticket, 0); in_batch = 0; }
-                    item = ticket < nbatches ? static_end + ticket * batch + in_batch : nitems;
-                    if (item < nitems && in_batch == 0 && lane == 0) next_ticket = atomicAdd(tickets, 1u) - tbase;   // hides behind this batch
-                    if (item >= nitems && ticket < nbatches) {       // ragged last batch: fetch the (overdrawn) next ticket
-                        ticket = __shfl_sync(FULL, next_ticket, 0);
-                        in_batch = 0;
-                        continue;
-                    }
-                    ++in_batch;
-                }
-                return item;
             }
-        };
-        struct Item { int g, sy, fl, sx0, ncell; };
-        auto decode = [&](unsigned item) -> Item {
-            const int chunk = (int)item / P.nrows;
-            const int row = (int)item - chunk * P.nrows;
-            Item it;
-            it.g = row / P.h;
-            it.sy = row - it.g * P.h;
-            it.fl = __ldg(P.fmap + it.g);
-            it.sx0 = chunk * FZ_CELLS;
-            it.ncell = min(FZ_CELLS, P.w - it.sx0);
-            return it;
-        };
-        while (true) {
-            const unsigned cur = next_item();
+            if (drawing) {
+                if (in_batch == batch) { ticket = __shfl_sync(FULL, next_ticket, 0); in_batch = 0; }
+                item = ticket < nbatches ? static_end + ticket * batch + in_batch : nitems;
+                if (item < nitems && in_batch == 0 && lane == 0) next_ticket = atomicAdd(tickets, 1u) - tbase;   // hides behind this batch
+                if (item >= nitems && ticket < nbatches) {       // ragged last batch: fetch the (overdrawn) next ticket
+                    ticket = __shfl_sync(FULL, next_ticket, 0);
+                    in_batch = 0;
+                    continue;
+                }
+                ++in_batch;
+            }
             mbar_wait(sbase + L::BAR_OFF + (FZ_STAGES + stage) * 8, ph ^ 1u);
             const uint32_t sb = sbase + stage * L::STAGE;
             const uint32_t full = sbase + L::BAR_OFF + stage * 8;
-            if (cur >= nitems) {                     // end marker for the consumers
+            if (item >= nitems) {                    // end marker for the consumers
                 if (lane == 0) {
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb + L::DESC_OFF), "r"(0), "r"(-1), "r"(0), "r"(0) : "memory");
+                    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sb + L::DESC_OFF), "r"(0), "r"(-1) : "memory");
                     mbar_arrive(full);
                 }
                 break;
             }
-            const Item it = decode(cur);
+            const int chunk = (int)item / P.nrows;
+            const int row = (int)item - chunk * P.nrows;
+            const int g = row / P.h;
+            const int sy = row - g * P.h;
+            const int fl = __ldg(P.fmap + g);
+            const int sx0 = chunk * FZ_CELLS;
+            const int ncell = min(FZ_CELLS, P.w - sx0);
             if (lane == 0) {
-                // descriptor: first cell of the stage in the winner array, cells in the stage
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb + L::DESC_OFF), "r"((it.fl * P.h + it.sy) * P.w + it.sx0),
-                             "r"(it.ncell), "r"(0), "r"(0) : "memory");
-                mbar_expect_tx(full, (uint32_t)(it.ncell * (64 * FzId<IdT>::PX + (with_x ? 4 * (int)sizeof(XT) : 0))));
+                asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sb + L::DESC_OFF), "r"((fl * P.h + sy) * P.w + sx0), "r"(ncell) : "memory");
+                mbar_expect_tx(full, (uint32_t)(ncell * (64 * FzId<IdT>::PX + (with_x ? 4 * (int)sizeof(XT) : 0))));
             }
             __syncwarp();
             if (lane < 8) {
-                const long long px = ((long long)it.g * P.H + it.sy * 8 + lane) * P.W + it.sx0 * 8;
-                bulk_g2s_hint(sb + lane * FzId<IdT>::PITCH, ids + px * FzId<IdT>::PX, (uint32_t)(it.ncell * 8 * FzId<IdT>::PX), full, pol);
+                const long long px = ((long long)g * P.H + sy * 8 + lane) * P.W + sx0 * 8;
+                bulk_g2s_hint(sb + lane * FzId<IdT>::PITCH, ids + px * FzId<IdT>::PX, (uint32_t)(ncell * 8 * FzId<IdT>::PX), full, pol);
             } else if (lane < 12 && with_x) {
-                // The stage's latents ride on the same barrier as four small bulk copies.  They cost ~10 % of the pure
-                // streaming rate (tools/streamprobe), but every alternative that goes through the load/store unit — plain
-                // loads by the consumers at the start of a stage, one stage ahead, or by this warp one item ahead — queues
-                // behind the consumers' reductions and was measured slower (profiles/r2_latent_fetch_variants.txt).
                 const int ch = lane - 8;
                 bulk_g2s(sb + L::LAT_OFF + ch * FZ_CELLS * (int)sizeof(XT),
-                         x + ((long long)(it.fl * 4 + ch) * P.h + it.sy) * P.w + it.sx0, (uint32_t)(it.ncell * (int)sizeof(XT)), full);
+                         x + ((long long)(fl * 4 + ch) * P.h + sy) * P.w + sx0, (uint32_t)(ncell * (int)sizeof(XT)), full);
             }
             if (++stage == FZ_STAGES) { stage = 0; ph ^= 1u; }
         }

@@ -261,7 +261,8 @@ static int legacy_impl(const srx_legacy_desc *d, const srx_legacy_args *a, cudaS
     b.status = reinterpret_cast<int *>(ws + L.status);
 
     SRX_CUDA_CHECK(cudaMemsetAsync(b.keys, 0xFF, (size_t)(L.next - L.keys), st));                       // keys = EMPTY, head = -1
-    SRX_CUDA_CHECK(cudaMemsetAsync(ws + L.zero_begin, 0, (size_t)(L.zero_end - L.zero_begin), st));    // sums, counts, status
+    // sums, counts, status (the status block stays sticky when its check is deferred)
+    SRX_CUDA_CHECK(cudaMemsetAsync(ws + L.zero_begin, 0, (size_t)(L.zero_end - L.zero_begin - (a->defer_status ? 256 : 0)), st));
 
     LegacyGeom g;
     g.T = d->frames; g.H = d->height; g.W = d->width; g.h = d->lat_h; g.w = d->lat_w; g.C = d->channels;
@@ -280,6 +281,7 @@ static int legacy_impl(const srx_legacy_desc *d, const srx_legacy_args *a, cudaS
     k_legacy_accum<IdT, XT><<<blocks(npx), 256, 0, st>>>(ids, x, a->view_normal_dev, b, g, npx);
     k_legacy_finalize<XT><<<blocks(L.ncell), 256, 0, st>>>(x, b, g, a->alpha, (float)(1.0 - (double)a->alpha), L.ncell);
     SRX_CUDA_CHECK(cudaGetLastError());
+    if (a->defer_status) return SRX_OK;           // no host sync: srx_legacy_check reports (and clears) the status later
     int st_host = 0;
     SRX_CUDA_CHECK(cudaMemcpyAsync(&st_host, b.status, sizeof(int), cudaMemcpyDeviceToHost, st));
     SRX_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -297,6 +299,25 @@ static int legacy_x_dispatch(const srx_legacy_desc *d, const srx_legacy_args *a,
         case SRX_BF16: return legacy_impl<IdT, __nv_bfloat16>(d, a, st);
         default: return srx_set_error(SRX_ERR_INVALID, "latent dtype must be f32/f16/bf16");
     }
+}
+
+// Deferred status (args->defer_status = 1): reads and clears the sticky status word of earlier srx_legacy_overlap calls on this
+// workspace (which must start zeroed); SRX_ERR_KEY_RANGE if any of them met an id that does not fit the packed key.  Syncs.
+extern "C" int srx_legacy_check(const srx_legacy_desc *d, const srx_legacy_args *a, void *stream) {
+    int rc = legacy_validate(d);
+    if (rc) return rc;
+    SRX_REQUIRE(a && a->workspace_dev, SRX_ERR_INVALID, "null buffer");
+    const LegacyLayout L = legacy_layout(d);
+    int *status = reinterpret_cast<int *>(reinterpret_cast<char *>(a->workspace_dev) + L.status);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int st_host = 0;
+    SRX_CUDA_CHECK(cudaMemcpyAsync(&st_host, status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SRX_CUDA_CHECK(cudaMemsetAsync(status, 0, 256, st));
+    SRX_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (st_host)
+        return srx_set_error(SRX_ERR_KEY_RANGE, "an id component does not fit the packed 64-bit key "
+                             "(int32 ids: sprite, material < 1024, third component < 4096 after merge, fourth >= 0)");
+    return SRX_OK;
 }
 
 extern "C" int srx_legacy_overlap(const srx_legacy_desc *d, const srx_legacy_args *a, void *stream) {

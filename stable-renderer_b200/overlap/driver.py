@@ -25,6 +25,9 @@ class Overlap:
         self.alpha_scheduler = alpha_scheduler
         self.kernel_radius_scheduler = kernel_radius_scheduler
         self._workspace: Optional[torch.Tensor] = None
+        self.defer_check = False
+        '''True: calls only enqueue kernels (no host sync); ids that do not fit the packed key are reported by `check()`'''
+        self._last = None
 
     @property
     def verbose(self):
@@ -58,8 +61,9 @@ class Overlap:
         if need < 0:
             _lib.check(_lib.SRX_ERR_INVALID)
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != stack.device:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=stack.device)
+            self._workspace = torch.zeros(need, dtype=torch.uint8, device=stack.device)
         a = _lib.srx_legacy_args()
+        a.defer_status = 1 if (self.defer_check and radius == 0) else 0
         a.x_dev, a.x_dtype = stack.data_ptr(), _lib.torch_dtype_code(stack.dtype)
         a.ids_dev = ids.data_ptr()
         a.alpha = float(alpha)
@@ -77,6 +81,16 @@ class Overlap:
                 _lib.check(lib.srx_legacy_overlap_ordered(C.byref(d), C.byref(a), int(radius), stream))
             else:
                 _lib.check(lib.srx_legacy_overlap(C.byref(d), C.byref(a), stream))
+                if a.defer_status:
+                    self._last = (d, a, stack.device)
+
+    def check(self) -> None:
+        """Raises for ids that did not fit the packed key in calls made with `defer_check = True` (syncs)."""
+        if self._last is None:
+            return
+        d, a, dev = self._last
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().srx_legacy_check(C.byref(d), C.byref(a), _lib.current_stream_ptr(dev)))
 
     def _schedule(self, step, timestep):
         """(alpha, kernel_radius) for this call (overlap.py:100-101: the radius is `int()`-truncated)."""

@@ -264,3 +264,27 @@ def test_view_sharded_bake_two_gpus():
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
     assert "BAKE_SHARD_OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
+
+
+def test_bake_deferred_status_check():
+    """`update(..., defer_check=True)` never syncs the host; an out-of-atlas texel is reported by `check()`, once."""
+    from stable_renderer_b200.corrmap import CorrespondMap
+    H = 16
+    ids = torch.zeros(1, H, H, 4, dtype=torch.int32)
+    ids[..., 0], ids[..., 3] = 1, torch.arange(H * H, dtype=torch.int32).view(H, H)
+    colors = torch.rand(1, H, H, 3)
+    cm = CorrespondMap(name="d", k=1, height=H, width=H, channel_count=4)
+    cm.update(colors.cuda(), ids.cuda(), mode="replace", ignore_obj_mat_id=True, defer_check=True)
+    cm.check()                                                     # all texels inside: nothing to report
+    ref = CorrespondMap(name="r", k=1, height=H, width=H, channel_count=4)
+    ref.update(colors.cuda(), ids.cuda(), mode="replace", ignore_obj_mat_id=True)
+    assert torch.equal(cm._values, ref._values) and torch.equal(cm._writtens, ref._writtens)
+    bad = ids.clone()
+    bad[0, 3, 3, 3] = H * H + 5                                    # vertex id outside the atlas
+    cm.update(colors.cuda(), bad.cuda(), mode="replace", ignore_obj_mat_id=True, defer_check=True)
+    cm.update(colors.cuda(), ids.cuda(), mode="replace", ignore_obj_mat_id=True, defer_check=True)    # the flag survives later calls
+    with pytest.raises(IndexError):
+        cm.check()
+    cm.check()                                                     # reported once, then cleared
+    with pytest.raises(IndexError):                                # the default stays the reference's behaviour
+        cm.update(colors.cuda(), bad.cuda(), mode="replace", ignore_obj_mat_id=True)
