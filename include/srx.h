@@ -469,6 +469,18 @@ int srx_feature_overlap(const srx_feature_args *args, void *stream);
 /* SRX_ERR_INDEX / SRX_ERR_KEY_RANGE for device-side failures of the last call on this workspace (syncs) */
 int srx_feature_overlap_check(const srx_feature_args *args, void *stream);
 
+/* Cell-similarity overlap — taichi_cells_overlap (source/common_utils/stable_render_utils/corr_utils.py:110-134): every cell
+ * becomes the similarity-weighted mean of all cells, similarity = sum over pixel pairs with identical id 4-tuples of the product of
+ * their contributions; a cell = pixels / cells consecutive pixels of the flattened frame.  Evaluated in the factorised form
+ * (per-key sums), two calls: srx_cells_overlap_keys counts the distinct id tuples (syncs; *n_keys_out on the host), the caller
+ * zero-allocates key_sums [n_keys * (channels + 1)] floats, srx_cells_overlap fills new_values (its content is added to, like the
+ * reference's placeholder).  ids [batch, pixels, 4] int32, contributions [batch, pixels] f32, values / new_values [batch, cells, c]. */
+int64_t srx_cells_overlap_workspace_bytes(int batch, int pixels);
+int srx_cells_overlap_keys(const int32_t *ids_dev, const float *contrib_dev, int batch, int pixels, int cells, void *workspace,
+                           int64_t workspace_bytes, int64_t *n_keys_out, void *stream);
+int srx_cells_overlap(const float *values_dev, float *new_values_dev, int batch, int pixels, int cells, int channels, void *workspace,
+                      float *key_sums_dev, int64_t n_keys, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

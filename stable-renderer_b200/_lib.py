@@ -145,6 +145,9 @@ _PROTOTYPES = {
     "srx_feature_overlap_workspace_bytes": (C.c_int64, [C.POINTER(srx_feature_args)]),
     "srx_feature_overlap": (C.c_int, [C.POINTER(srx_feature_args), C.c_void_p]),
     "srx_feature_overlap_check": (C.c_int, [C.POINTER(srx_feature_args), C.c_void_p]),
+    "srx_cells_overlap_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "srx_cells_overlap_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
+    "srx_cells_overlap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "srx_plan_read_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "srx_plan_read_step_ring": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "srx_plan_destroy": (C.c_int, [C.c_void_p]),

@@ -370,3 +370,171 @@ extern "C" int srx_feature_overlap_check(const srx_feature_args *a, void *stream
     if (host[FO_ST_RANGE] & 2) return srx_set_error(SRX_ERR_KEY_RANGE, "a vertex id fell outside the key capacity (%lld)", (long long)a->key_capacity);
     return SRX_OK;
 }
+
+// =====================================================================================================================
+// Cell-similarity overlap — taichi_cells_overlap (source/common_utils/stable_render_utils/corr_utils.py:110-134).
+// new[A] = (new[A] + val[A] + sum_{B != A} sim(A,B) val[B]) * (1 / (1 + sum_{B != A} sim(A,B))),
+// sim(A,B) = sum_{x in A, i in B} contrib[x] contrib[i] [id[x] == id[i]]  (all four components; no validity filter, :28-44);
+// a cell = pixels // cells CONSECUTIVE pixels of the flattened frame (:130).  The reference loops over all cell pairs and all
+// pixel pairs (O(cells^2 px^2)); with c_A[key] = the summed contribution of A's pixels that carry `key`,
+//     sim(A,B) = sum_key c_A[key] c_B[key]   =>   sum_{B != A} sim(A,B) val[B] = sum_key c_A[key] (S[key] - c_A[key] val[A]),
+//     S[key] = sum_B c_B[key] val[B],  T[key] = sum_B c_B[key]   —   linear in pixels + pairs.
+//   k_cs_insert   id tuple -> open-addressing table (exact 64-bit packing), dense rank per distinct key
+//   k_cs_pairs    a warp per cell: the distinct keys of the cell with their summed contributions (leader pixel per key)
+//   k_cs_scatter  S[key] += c * val[cell] (channels over the threads), T[key] += c
+//   k_cs_finish   the formula above per cell
+// =====================================================================================================================
+#define CS_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+__device__ __forceinline__ bool cs_pack(const int4 &p, unsigned long long *key) {
+    if (p.x < 0 || p.x >= 1024 || p.y < 0 || p.y >= 1024 || p.z < 0 || p.z >= 4096 || p.w < 0) return false;
+    *key = ((unsigned long long)p.x << 54) | ((unsigned long long)p.y << 44) | ((unsigned long long)p.z << 32) | (unsigned long long)(unsigned)p.w;
+    return true;
+}
+__device__ __forceinline__ unsigned cs_hash(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (unsigned)k;
+}
+
+__global__ void __launch_bounds__(256) k_cs_insert(const int4 *__restrict__ ids, long long npx_total, unsigned long long *keys,
+                                                    int *__restrict__ rank_of, int *__restrict__ px_slot, unsigned mask, int *counters) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npx_total; p += (long long)gridDim.x * blockDim.x) {
+        unsigned long long key;
+        int slot = -1;
+        if (!cs_pack(ids[p], &key)) atomicOr(counters + 1, 1);
+        else {
+            unsigned s = cs_hash(key) & mask;
+            while (true) {
+                const unsigned long long prev = atomicCAS(keys + s, CS_EMPTY, key);
+                if (prev == CS_EMPTY) { rank_of[s] = atomicAdd(counters, 1); break; }
+                if (prev == key) break;
+                s = (s + 1) & mask;
+            }
+            slot = (int)s;
+        }
+        px_slot[p] = slot;
+    }
+}
+
+// pair_rank / pair_w [cells_total][cpp]: entry j of a cell is (rank, summed contribution) when pixel j is the first of the
+// cell with its key, else rank = -1
+__global__ void __launch_bounds__(256) k_cs_pairs(const int *__restrict__ px_slot, const int *__restrict__ rank_of, const float *__restrict__ contrib,
+                                                   long long cells_total, int cells, int cpp, int npx, int *__restrict__ pair_rank,
+                                                   float *__restrict__ pair_w) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long cell = warp; cell < cells_total; cell += nwarps) {
+        const long long b = cell / cells, ci = cell - b * cells;
+        const long long base = b * npx + ci * cpp;
+        for (int j = lane; j < cpp; j += 32) {
+            const int sj = px_slot[base + j];
+            bool leader = sj >= 0;
+            for (int i = 0; i < j && leader; ++i) leader = px_slot[base + i] != sj;
+            float w = 0.f;
+            if (leader)
+                for (int i = j; i < cpp; ++i) if (px_slot[base + i] == sj) w += contrib[base + i];
+            pair_rank[cell * cpp + j] = leader ? rank_of[sj] : -1;
+            pair_w[cell * cpp + j] = w;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_cs_scatter(const float *__restrict__ val, const int *__restrict__ pair_rank, const float *__restrict__ pair_w,
+                                                     int cpp, int c, float *__restrict__ S, float *__restrict__ T) {
+    const long long cell = blockIdx.x;
+    for (int j = 0; j < cpp; ++j) {
+        const int r = pair_rank[cell * cpp + j];
+        if (r < 0) continue;
+        const float w = pair_w[cell * cpp + j];
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) red_add_f32(S + (long long)r * c + ch, __fmul_rn(w, val[cell * c + ch]));
+        if (threadIdx.x == 0) red_add_f32(T + r, w);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_cs_finish(const float *__restrict__ val, const int *__restrict__ pair_rank, const float *__restrict__ pair_w,
+                                                    int cpp, int c, const float *__restrict__ S, const float *__restrict__ T, float *__restrict__ out) {
+    const long long cell = blockIdx.x;
+    float den = 1.f;
+    for (int j = 0; j < cpp; ++j) {
+        const int r = pair_rank[cell * cpp + j];
+        if (r >= 0) { const float w = pair_w[cell * cpp + j]; den += w * (T[r] - w); }
+    }
+    const float inv = __fdiv_rn(1.f, den);                  // corr_utils.py:108: values *= 1.0 / total_sim
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        const float v = val[cell * c + ch];
+        float num = out[cell * c + ch] + v;                 // :85-90: the target cell's own value is added to the placeholder first
+        for (int j = 0; j < cpp; ++j) {
+            const int r = pair_rank[cell * cpp + j];
+            if (r >= 0) { const float w = pair_w[cell * cpp + j]; num += w * (S[(long long)r * c + ch] - w * v); }
+        }
+        out[cell * c + ch] = __fmul_rn(num, inv);
+    }
+}
+
+static inline int64_t cs_cap(int64_t npx_total) { int64_t cap = 1024; while (cap < 2 * npx_total) cap <<= 1; return cap; }
+
+// workspace of the key pass: [counters 256][keys cap*8][rank_of cap*4][px_slot npx*4][pair_rank npx*4][pair_w npx*4]
+extern "C" int64_t srx_cells_overlap_workspace_bytes(int batch, int pixels) {
+    if (batch <= 0 || pixels <= 0) return -1;
+    const int64_t n = (int64_t)batch * pixels, cap = cs_cap(n);
+    return 256 + fo_align(cap * 8) + fo_align(cap * 4) + 3 * fo_align(n * 4);
+}
+
+// Pass 1: distinct id tuples -> *n_keys_out (host; syncs) — the caller then allocates the [n_keys, c] + [n_keys] float key sums.
+extern "C" int srx_cells_overlap_keys(const int32_t *ids_dev, const float *contrib_dev, int batch, int pixels, int cells, void *workspace,
+                                      int64_t workspace_bytes, int64_t *n_keys_out, void *stream) {
+    SRX_REQUIRE(ids_dev && contrib_dev && workspace && n_keys_out, SRX_ERR_INVALID, "null argument");
+    SRX_REQUIRE(batch > 0 && pixels > 0 && cells > 0 && pixels >= cells, SRX_ERR_INVALID, "bad sizes");
+    SRX_REQUIRE(workspace_bytes >= srx_cells_overlap_workspace_bytes(batch, pixels), SRX_ERR_INVALID, "workspace too small");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t n = (int64_t)batch * pixels, cap = cs_cap(n);
+    char *ws = reinterpret_cast<char *>(workspace);
+    int *counters = reinterpret_cast<int *>(ws);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws + 256);
+    int *rank_of = reinterpret_cast<int *>(ws + 256 + fo_align(cap * 8));
+    int *px_slot = rank_of + fo_align(cap * 4) / 4;
+    int *pair_rank = px_slot + fo_align(n * 4) / 4;
+    float *pair_w = reinterpret_cast<float *>(pair_rank + fo_align(n * 4) / 4);
+    SRX_CUDA_CHECK(cudaMemsetAsync(counters, 0, 256, st));
+    SRX_CUDA_CHECK(cudaMemsetAsync(keys, 0xFF, (size_t)cap * 8, st));
+    const int sms = srx_sm_count_cached();
+    const long long nb = (n + 255) / 256;
+    k_cs_insert<<<(int)(nb < (long long)sms * 16 ? nb : (long long)sms * 16), 256, 0, st>>>(reinterpret_cast<const int4 *>(ids_dev), n, keys, rank_of,
+                                                                                             px_slot, (unsigned)(cap - 1), counters);
+    const int cpp = pixels / cells;
+    const long long cells_total = (long long)batch * cells;
+    // pixels past cells * cpp belong to no cell (corr_utils.py:130) — the pair pass never reads them
+    const long long nbw = (cells_total * 32 + 255) / 256;
+    k_cs_pairs<<<(int)(nbw < (long long)sms * 16 ? nbw : (long long)sms * 16), 256, 0, st>>>(px_slot, rank_of, contrib_dev, cells_total, cells, cpp, pixels,
+                                                                                              pair_rank, pair_w);
+    SRX_CUDA_CHECK(cudaGetLastError());
+    int host[2] = {0, 0};
+    SRX_CUDA_CHECK(cudaMemcpyAsync(host, counters, sizeof(host), cudaMemcpyDeviceToHost, st));
+    SRX_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (host[1]) return srx_set_error(SRX_ERR_KEY_RANGE, "an id component does not fit the packed 64-bit key (sprite, material < 1024, "
+                                      "map index < 4096, vertex id >= 0)");
+    *n_keys_out = host[0];
+    return SRX_OK;
+}
+
+// Pass 2: values [batch, cells, c] f32, new_values [batch, cells, c] f32 (the reference's placeholder: its content is added to,
+// corr_utils.py:85-90), key_sums = zeroed [n_keys * (c + 1)] floats.
+extern "C" int srx_cells_overlap(const float *values_dev, float *new_values_dev, int batch, int pixels, int cells, int channels, void *workspace,
+                                 float *key_sums_dev, int64_t n_keys, void *stream) {
+    SRX_REQUIRE(values_dev && new_values_dev && workspace && key_sums_dev, SRX_ERR_INVALID, "null argument");
+    SRX_REQUIRE(batch > 0 && pixels > 0 && cells > 0 && channels > 0 && n_keys >= 0, SRX_ERR_INVALID, "bad sizes");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t n = (int64_t)batch * pixels, cap = cs_cap(n);
+    char *ws = reinterpret_cast<char *>(workspace);
+    int *rank_of = reinterpret_cast<int *>(ws + 256 + fo_align(cap * 8));
+    int *px_slot = rank_of + fo_align(cap * 4) / 4;
+    int *pair_rank = px_slot + fo_align(n * 4) / 4;
+    float *pair_w = reinterpret_cast<float *>(pair_rank + fo_align(n * 4) / 4);
+    float *S = key_sums_dev, *T = key_sums_dev + n_keys * channels;
+    const int cpp = pixels / cells;
+    const unsigned cells_total = (unsigned)((long long)batch * cells);
+    k_cs_scatter<<<cells_total, 128, 0, st>>>(values_dev, pair_rank, pair_w, cpp, channels, S, T);
+    k_cs_finish<<<cells_total, 128, 0, st>>>(values_dev, pair_rank, pair_w, cpp, channels, S, T, new_values_dev);
+    SRX_CUDA_CHECK(cudaGetLastError());
+    return SRX_OK;
+}

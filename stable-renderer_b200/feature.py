@@ -61,4 +61,32 @@ def feature_overlap(origin_values: torch.Tensor, id_map: IDMap, ratio: float = 0
     return out
 
 
-__all__ = ["feature_overlap", "POST_ATTN_SKIP_LAYERS"]
+def taichi_cells_overlap(id_flatten_maps: torch.Tensor, origin_values: torch.Tensor, new_values: torch.Tensor,
+                         contributions: torch.Tensor) -> None:
+    """`taichi_cells_overlap(id_flatten_maps, origin_values, new_values, contributions)` (reference corr_utils.py:110-134): fills
+    `new_values` [b, cells, c] (float32, in place — its content is added to, like the reference's placeholder) with the
+    similarity-weighted mean over all cells.  id_flatten_maps [b, pixels, 4] (any integer-valued dtype), contributions [b, pixels].
+    Linear in pixels and distinct (cell, key) pairs instead of the reference's loop over all pixel pairs of all cell pairs."""
+    if not (origin_values.is_cuda and new_values.is_cuda):
+        raise _lib.SrxUnavailable("values must live on a CUDA device (there is no CPU path)")
+    if new_values.dtype != torch.float32 or not new_values.is_contiguous() or new_values.shape != origin_values.shape:
+        raise ValueError("new_values must be a contiguous float32 tensor of origin_values' shape")
+    dev = new_values.device
+    b, cells, c = (int(v) for v in origin_values.shape)
+    pixels = int(id_flatten_maps.shape[1])
+    ids = id_flatten_maps.to(device=dev, dtype=torch.int32).contiguous()
+    contrib = contributions.to(device=dev, dtype=torch.float32).contiguous()
+    vals = origin_values.to(torch.float32).contiguous()
+    lib = _lib.load()
+    nbytes = int(lib.srx_cells_overlap_workspace_bytes(b, pixels))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    n_keys = C.c_int64(0)
+    with torch.cuda.device(dev):
+        stream = _lib.current_stream_ptr(dev)
+        _lib.check(lib.srx_cells_overlap_keys(ids.data_ptr(), contrib.data_ptr(), b, pixels, cells, ws.data_ptr(), nbytes, C.byref(n_keys), stream))
+        sums = torch.zeros(max(int(n_keys.value), 1) * (c + 1), dtype=torch.float32, device=dev)
+        _lib.check(lib.srx_cells_overlap(vals.data_ptr(), new_values.data_ptr(), b, pixels, cells, c, ws.data_ptr(), sums.data_ptr(),
+                                         int(n_keys.value), stream))
+
+
+__all__ = ["feature_overlap", "taichi_cells_overlap", "POST_ATTN_SKIP_LAYERS"]

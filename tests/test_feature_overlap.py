@@ -87,3 +87,28 @@ def test_gpu_post_atten_inject_switch_and_errors():
         feature_overlap(feats, IDMap(tensor=ids), key_capacity=8)                              # vertex ids beyond the capacity
     with pytest.raises(IndexError):
         feature_overlap(feats, IDMap(tensor=ids, frame_indices=[0, 5]))                        # frame index outside the batch
+
+
+@pytest.mark.gpu
+def test_gpu_cells_overlap_vs_taichi_kernel(golden):
+    from stable_renderer_b200.feature import taichi_cells_overlap
+    g = golden("feature_overlap")
+    new = torch.zeros(g["cells_values"].shape, dtype=torch.float32, device="cuda")
+    taichi_cells_overlap(torch.from_numpy(g["cells_ids"]).cuda(), torch.from_numpy(g["cells_values"]).cuda(), new,
+                         torch.from_numpy(g["cells_contrib"]).cuda())
+    assert_close(t2n(new), g["cells_new"], 2e-5, 5e-6, "cells overlap")
+
+
+@pytest.mark.gpu
+def test_gpu_cells_overlap_vs_oracle_wide():
+    """2 frames of 64x64 pixels, 8x8 latent cells' worth of 64-pixel runs, 320 channels, background pixels included."""
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.feature import taichi_cells_overlap
+    ids = synthetic.make_ids(2, 64, 64, tex_h=12, tex_w=12, seed=91).reshape(2, 64 * 64, 4)
+    gen = torch.Generator().manual_seed(2)
+    vals = torch.randn(2, 64, 320, generator=gen)
+    contrib = torch.rand(2, 64 * 64, generator=gen) / 64
+    want = O.cells_overlap(ids.numpy(), vals.numpy(), contrib.numpy())
+    new = torch.zeros_like(vals).cuda()
+    taichi_cells_overlap(ids.cuda(), vals.cuda(), new, contrib.cuda())
+    assert_close(t2n(new), want, 5e-5, 1e-5, "cells overlap wide")
