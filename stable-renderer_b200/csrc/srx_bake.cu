@@ -162,6 +162,80 @@ __global__ void __launch_bounds__(256) k_bake_claim_pair(const IdT *__restrict__
     bake_claim_texel0(zmax, writtens, owner, g);
 }
 
+// The same pass as a three-stage software pipeline: in one loop round a thread requests the ids of round n+1, issues the owner
+// probes of round n and consumes the probes of round n-1, so neither of the two dependent round trips (ids -> texel, texel -> owner
+// word) is waited for in the round that issued it.  (ncu source view of k_bake_claim_pair on config 4: 58 % of all warp samples
+// sit on the compare that consumes the owner word, profiles/r2_bake_claim_pair_stalls.txt.)  MODE 1 skips the probe and issues
+// the atomicMax for every kept pixel (no dependent load at all, four times the atomics).
+template <typename IdT, int MODE>
+__global__ void __launch_bounds__(256) k_bake_claim_pipe(const IdT *__restrict__ ids, const float *__restrict__ masks,
+                                                          const uint8_t *__restrict__ writtens, unsigned int *__restrict__ owner,
+                                                          int *__restrict__ status, BakeGeom g, long long ngroups) {
+    const unsigned int hw = (unsigned int)((long long)g.H * g.W);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned int zmax = 0u;
+    long long gr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    IdPx px[2], nx[2];
+    float m[2], nm[2];
+    long long pt[2] = {0, 0};
+    unsigned int pcur[2] = {0u, 0u}, pord[2] = {0u, 0u};
+    bool pok[2] = {false, false};
+    if (gr < ngroups) bake_load_group<IdT, 1>(ids, masks, gr * 2, px, m);
+    while (gr < ngroups) {
+        if (gr + stride < ngroups) bake_load_group<IdT, 1>(ids, masks, (gr + stride) * 2, nx, nm);
+        const long long i0 = gr * 2;
+        long long t[2];
+        unsigned int cur[2], ord[2];
+        bool ok[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            t[k] = 0;
+            ok[k] = bake_texel_eval(px[k], m[k], masks != nullptr, g, false, &t[k], status);
+            ord[k] = bake_order1((unsigned int)i0 + (unsigned int)k + g.pix_offset, hw, g);
+            if (ok[k] && t[k] == 0) { zmax = ord[k] > zmax ? ord[k] : zmax; ok[k] = false; }
+        }
+        if (ok[0] && ok[1] && t[0] == t[1] && ord[1] > ord[0]) ok[0] = false;     // the neighbour's larger key makes this claim redundant
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            cur[k] = 0u;
+            if (ok[k] && g.first_mode && writtens[t[k]]) ok[k] = false;
+            if (MODE == 1) { if (ok[k]) atomicMax(owner + t[k], ord[k]); }
+            else if (ok[k]) cur[k] = __ldcg(owner + t[k]);
+        }
+        if (MODE != 1) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (pok[k] && pcur[k] < pord[k]) atomicMax(owner + pt[k], pord[k]);
+                pt[k] = t[k]; pcur[k] = cur[k]; pord[k] = ord[k]; pok[k] = ok[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { px[k] = nx[k]; m[k] = nm[k]; }
+        gr += stride;
+    }
+    if (MODE != 1) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (pok[k] && pcur[k] < pord[k]) atomicMax(owner + pt[k], pord[k]);
+    }
+    bake_claim_texel0(zmax, writtens, owner, g);
+}
+
+// Which form of the claim pass runs.  Config 4 (64 M pixels onto 16.7 M texels), ms per `replace` bake: probes consumed in the round
+// that issued them 0.407, consumed a round later 0.376, no probes 0.355 (profiles/r2_bake_claim_pair_stalls.txt) — an atomic is
+// fire-and-forget, a probe is a dependent round trip.  Probes pay when most claims are redundant (many more pixels than texels:
+// the atomics on one word serialise), so the probe-free form runs up to 16 pixels per texel.  SRX_BAKE_CLAIM = 0 | 1 | 2 forces
+// probe / no probe / pipelined probe.
+template <typename IdT>
+static void bake_launch_claim_pair(int grid, cudaStream_t st, const IdT *ids, const float *masks, const uint8_t *writtens,
+                                   unsigned int *owner, int *status, const BakeGeom &g, long long ngroups, long long ntex) {
+    const char *e = getenv("SRX_BAKE_CLAIM");
+    const int mode = e ? atoi(e) : (2 * ngroups <= 16 * ntex ? 1 : 0);
+    if (mode == 1) k_bake_claim_pipe<IdT, 1><<<grid, 256, 0, st>>>(ids, masks, writtens, owner, status, g, ngroups);
+    else if (mode == 2) k_bake_claim_pipe<IdT, 2><<<grid, 256, 0, st>>>(ids, masks, writtens, owner, status, g, ngroups);
+    else k_bake_claim_pair<IdT, 1><<<grid, 256, 0, st>>>(ids, masks, writtens, owner, status, g, ngroups);
+}
+
 template <typename CT> __device__ __forceinline__ float color_ld(const CT *p);
 template <> __device__ __forceinline__ float color_ld<float>(const float *p) { return __ldg(p); }
 template <> __device__ __forceinline__ float color_ld<__half>(const __half *p) { return __half2float(*p); }
@@ -376,7 +450,7 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
                 if (pair_ok) {
                     long long nbp = (npx / 2 + 255) / 256;
                     const int gridp = (int)(nbp < (long long)sms * 8 ? nbp : (long long)sms * 8);
-                    k_bake_claim_pair<IdT, 1><<<gridp, 256, 0, st>>>(ids, a->masks_dev, a->writtens_dev, owner, status, g, npx / 2);
+                    bake_launch_claim_pair<IdT>(gridp, st, ids, a->masks_dev, a->writtens_dev, owner, status, g, npx / 2, ntex);
                 } else {
                     k_bake_claim<IdT><<<grid, 256, 0, st>>>(ids, a->masks_dev, a->writtens_dev, owner, status, g, npx);
                 }
@@ -413,7 +487,7 @@ static int bake_impl(const srx_bake_args *a, cudaStream_t st) {
             if (pair_ok) {   // NP = 2 (four pixels per thread) measured 5 % slower on config 4: 0.436 against 0.415 ms per bake
                 long long nbp = (npx / 2 + 255) / 256;
                 const int gridp = (int)(nbp < (long long)sms * 8 ? nbp : (long long)sms * 8);
-                k_bake_claim_pair<IdT, 1><<<gridp, 256, 0, st>>>(ids + (long long)f0 * hw, masks, a->writtens_dev, owner, status, g, npx / 2);
+                bake_launch_claim_pair<IdT>(gridp, st, ids + (long long)f0 * hw, masks, a->writtens_dev, owner, status, g, npx / 2, ntex);
             } else {
                 k_bake_claim<IdT><<<grid, 256, 0, st>>>(ids + (long long)f0 * hw, masks, a->writtens_dev, owner, status, g, npx);
             }
