@@ -140,6 +140,7 @@ def init_dist(n_gpus: int):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner must not land on stdout beside the JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     elif n_gpus > 1:
@@ -783,6 +784,53 @@ def cpu_bake_baseline(views: int = 4) -> dict:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def run_feature_overlap(local: int) -> dict:
+    """SURVEY.md 8f-4 (the body of post_atten_inject): 16 frames of 512^2 ids, the three attention sizes of an SD1.5 UNet at 512^2,
+    fp16 features.  Per size: one call with cached buckets (every layer / denoise step after the first of an id batch) and one that
+    buckets the ids as well; algorithmic bytes = (rows gathered + 3 B h w) rows of c * 2 bytes (+ 16 B per id pixel when bucketing)."""
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import IDMap
+    from stable_renderer_b200.feature import feature_overlap
+    dev = torch.device("cuda", local)
+    F, H = 16, 512
+    ids = synthetic.make_ids(F, H, H, tex_h=512, tex_w=512, n_obj=1, frac_2048=0.05, seed=7, device=dev)
+    idm = IDMap(tensor=ids, frame_indices=list(range(F)))
+    peak, _ = measured_hbm_peak()
+
+    def timed(fn, reps=20, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    sizes = {}
+    for h, c in ((64, 320), (32, 640), (16, 1280)):
+        x = torch.randn(F, h * h, c, device=dev).to(torch.float16)
+        kw = dict(map_size=(H, H), key_capacity=512 * 512, check=False)
+        info = {}
+        feature_overlap(x, idm, 0.6, info=info, **kw)
+        row = c * 2
+        apply_bytes = (info["rows_gathered"] + 3 * F * h * h) * row
+        id_bytes = ids.numel() * ids.element_size()
+        ms_cached = timed(lambda: feature_overlap(x, idm, 0.6, **kw))
+        ms_bucket = timed(lambda: feature_overlap(x, idm, 0.6, cache_buckets=False, **kw))
+        sizes[f"hw{h}x{h}_c{c}"] = {
+            "ms_per_call": ms_cached, "algorithmic_bytes": apply_bytes, "rows_gathered": info["rows_gathered"],
+            "achieved_gbs": apply_bytes / ms_cached / 1e6, "roofline_frac": apply_bytes / ms_cached / 1e6 / peak,
+            "ms_per_call_bucketing_every_call": ms_bucket, "algorithmic_bytes_bucketing": apply_bytes + id_bytes}
+    return {"workload": f"feature overlap: {F} frames of {H}x{H} ids, [B, h*w, c] fp16 features, ratio 0.6, up-sampling size = id map size",
+            "api": "feature.feature_overlap(origin_values, id_map, ratio, map_size)  (OverlapCorresponder.post_atten_inject body)",
+            "timing": "CUDA events around the public call (host side included), median of 20", "dtype": "f16", "sizes": sizes}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -862,6 +910,8 @@ def main():
                     extra[key] = {k: r4[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "config", "roofline", "e2e",
                                                      "texels_per_sec", "dtype")}
                     torch.cuda.empty_cache()
+                extra["feature_overlap"] = run_feature_overlap(local)
+                torch.cuda.empty_cache()
             out["extra"] = extra
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline and args.workload == "bake":

@@ -463,11 +463,19 @@ typedef struct srx_feature_args {
     int64_t key_capacity;       /* vertex ids must be < key_capacity */
     void *workspace;            /* srx_feature_overlap_workspace_bytes(), 256-byte aligned */
     int64_t workspace_bytes;
+    int reuse_buckets;          /* 0: bucket the ids (one pass + one sort) and apply.  1: `workspace` still holds the buckets of an
+                                 * earlier call with the same ids, frame map, sizes (batch, lat_*, map_*) and key capacity — the ids are
+                                 * not read; channels, dtype, ratio and the features are free to differ (every attention layer and
+                                 * every denoise step of a sampling run sees the same ids).  Only the first
+                                 * srx_feature_overlap_bucket_bytes() bytes of the workspace are needed then. */
 } srx_feature_args;
 int64_t srx_feature_overlap_workspace_bytes(const srx_feature_args *args);
+int64_t srx_feature_overlap_bucket_bytes(const srx_feature_args *args);
 int srx_feature_overlap(const srx_feature_args *args, void *stream);
-/* SRX_ERR_INDEX / SRX_ERR_KEY_RANGE for device-side failures of the last call on this workspace (syncs) */
+/* SRX_ERR_INDEX / SRX_ERR_KEY_RANGE for device-side failures of the bucketing pass behind this workspace (syncs) */
 int srx_feature_overlap_check(const srx_feature_args *args, void *stream);
+/* feature rows the last call on this workspace gathered (its L2-side work; syncs); -1 on failure */
+int64_t srx_feature_overlap_rows(const srx_feature_args *args, void *stream);
 
 /* Cell-similarity overlap — taichi_cells_overlap (source/common_utils/stable_render_utils/corr_utils.py:110-134): every cell
  * becomes the similarity-weighted mean of all cells, similarity = sum over pixel pairs with identical id 4-tuples of the product of

@@ -94,7 +94,7 @@ class srx_feature_args(C.Structure):
                 ("frame_map_dev", C.c_void_p), ("feat_dev", C.c_void_p), ("out_dev", C.c_void_p), ("x_dtype", C.c_int),
                 ("batch", C.c_int), ("lat_h", C.c_int), ("lat_w", C.c_int), ("channels", C.c_int), ("map_height", C.c_int),
                 ("map_width", C.c_int), ("ratio", C.c_float), ("key_capacity", C.c_int64), ("workspace", C.c_void_p),
-                ("workspace_bytes", C.c_int64)]
+                ("workspace_bytes", C.c_int64), ("reuse_buckets", C.c_int)]
 
 
 class srx_gbuffer_arrays(C.Structure):
@@ -143,7 +143,9 @@ _PROTOTYPES = {
     "srx_plan_set_grid": (C.c_int, [C.c_void_p, C.c_int]),
     "srx_plan_bind_multicast": (C.c_int, [C.c_void_p, C.c_void_p]),
     "srx_feature_overlap_workspace_bytes": (C.c_int64, [C.POINTER(srx_feature_args)]),
+    "srx_feature_overlap_bucket_bytes": (C.c_int64, [C.POINTER(srx_feature_args)]),
     "srx_feature_overlap": (C.c_int, [C.POINTER(srx_feature_args), C.c_void_p]),
+    "srx_feature_overlap_rows": (C.c_int64, [C.POINTER(srx_feature_args), C.c_void_p]),
     "srx_feature_overlap_check": (C.c_int, [C.POINTER(srx_feature_args), C.c_void_p]),
     "srx_cells_overlap_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "srx_cells_overlap_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),

@@ -57,6 +57,7 @@ class IDMap:
     masks: Tensor = attrib(default=None)
     _vertex_screen_info_cache: Tensor = attrib(default=None, init=False)
     _plans: dict = attrib(factory=dict, init=False, repr=False)
+    _feature_buckets: dict = attrib(factory=dict, init=False, repr=False)     # feature.py: bucketing passes of the feature overlap
     _device_ids: dict = attrib(factory=dict, init=False, repr=False)
 
     @property
@@ -164,6 +165,7 @@ class IDMap:
         (corrmap.py:226,278) and avoids it by building a new IDMap per batch; this keeps plans (and, frame-sharded, their
         symmetric-memory workspaces) alive across batches."""
         self._vertex_screen_info_cache = None
+        self._feature_buckets.clear()
         same = self._device_ids.get(self.tensor.device) if isinstance(self.tensor, Tensor) else None
         self._device_ids = {self.tensor.device: same} if same is not None and same.data_ptr() == self.tensor.data_ptr() else {}
         for key, plan in list(self._plans.items()):

@@ -17,13 +17,18 @@ POST_ATTN_SKIP_LAYERS = tuple(range(11))     # corresponder.py:232-234: "post at
 
 
 def feature_overlap(origin_values: torch.Tensor, id_map: IDMap, ratio: float = 0.6,
-                    map_size: Optional[Tuple[int, int]] = None, key_capacity: int = 0, check: bool = True) -> torch.Tensor:
+                    map_size: Optional[Tuple[int, int]] = None, key_capacity: int = 0, check: bool = True,
+                    cache_buckets: bool = True, info: Optional[dict] = None) -> torch.Tensor:
     """origin_values [B, h*w, c] (h*w a perfect square) -> new tensor of the same shape and dtype.
 
     map_size: the (height, width) the features are up-sampled to before the per-pixel gather.  The reference passes
               `(id_map.height, id_map.width)`, which for `[F,H,W,4]` ids are `(W, 4)` (corrmap.py:85-93) — the default here,
               to stay a drop-in; `(H, W)` is what the comment in the reference intends ("match the size of the id map").
-    key_capacity: exclusive upper bound of the vertex ids; 0 = one `max()` over the ids (syncs)."""
+    key_capacity: exclusive upper bound of the vertex ids; 0 = one `max()` over the ids (syncs, first call per id batch only).
+    cache_buckets: keep the result of the bucketing pass (one id pass + one sort; depends on the ids, the frame indices and the sizes,
+              not on the features) on the IDMap — every attention layer of that size and every denoise step of the run reuses it;
+              `IDMap.invalidate()` drops it.  False = bucket on every call (nothing is kept).
+    info: if a dict, receives `rows_gathered` and `buckets_reused` (one sync)."""
     if not origin_values.is_cuda:
         raise _lib.SrxUnavailable("features must live on a CUDA device (there is no CPU path)")
     if origin_values.dim() != 3:
@@ -36,28 +41,48 @@ def feature_overlap(origin_values: torch.Tensor, id_map: IDMap, ratio: float = 0
     ids = id_map.device_ids(dev)
     F, H, W = int(ids.shape[0]), int(ids.shape[1]), int(ids.shape[2])
     mh, mw = (int(id_map.height), int(id_map.width)) if map_size is None else (int(map_size[0]), int(map_size[1]))
+    frame_indices = tuple(int(v) for v in id_map.frame_indices)
+    buckets = id_map._feature_buckets if cache_buckets else {}
     if key_capacity <= 0:
-        key_capacity = int(ids[..., 3].max().item()) + 1
+        key_capacity = buckets.get(("max_key", dev))
+        if key_capacity is None:
+            key_capacity = int(ids[..., 3].max().item()) + 1
+            buckets[("max_key", dev)] = key_capacity
+    bkey = (dev, ids.data_ptr(), frame_indices, B, h, mh, mw, int(key_capacity))
     feat = origin_values.contiguous()
     out = torch.empty_like(feat)
-    fmap = torch.tensor([int(v) for v in id_map.frame_indices], dtype=torch.int32, device=dev)
     lib = _lib.load()
     a = _lib.srx_feature_args()
     a.ids_dev, a.id_dtype, a.frames, a.height, a.width = ids.data_ptr(), _lib.torch_dtype_code(ids.dtype), F, H, W
-    a.frame_map_dev = fmap.data_ptr()
     a.feat_dev, a.out_dev, a.x_dtype = feat.data_ptr(), out.data_ptr(), _lib.torch_dtype_code(feat.dtype)
     a.batch, a.lat_h, a.lat_w, a.channels = B, h, h, c
     a.map_height, a.map_width, a.ratio, a.key_capacity = mh, mw, float(ratio), int(key_capacity)
-    nbytes = int(lib.srx_feature_overlap_workspace_bytes(C.byref(a)))
-    if nbytes < 0:
-        _lib.check(_lib.SRX_ERR_INVALID if c * feat.element_size() % 16 == 0 and c <= 1280 else _lib.SRX_ERR_UNSUPPORTED)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    ws = buckets.get(bkey)
+    reuse = ws is not None
+    if not reuse:
+        nbytes = int(lib.srx_feature_overlap_workspace_bytes(C.byref(a)))
+        if nbytes < 0:
+            _lib.check(_lib.SRX_ERR_INVALID if c * feat.element_size() % 16 == 0 and c <= 1280 else _lib.SRX_ERR_UNSUPPORTED)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        fmap = torch.tensor(frame_indices, dtype=torch.int32, device=dev)
+        a.frame_map_dev = fmap.data_ptr()
+    elif c * feat.element_size() % 16 != 0 or c > 1280:
+        _lib.check(_lib.SRX_ERR_UNSUPPORTED)
+    a.workspace, a.workspace_bytes, a.reuse_buckets = ws.data_ptr(), int(ws.numel()), int(reuse)
     with torch.cuda.device(dev):
         stream = _lib.current_stream_ptr(dev)
         _lib.check(lib.srx_feature_overlap(C.byref(a), stream))
-        if check:
-            _lib.check(lib.srx_feature_overlap_check(C.byref(a), stream))
+        if check and not reuse:
+            _lib.check(lib.srx_feature_overlap_check(C.byref(a), stream))      # range failures belong to the bucketing pass
+        if info is not None:
+            info["rows_gathered"] = int(lib.srx_feature_overlap_rows(C.byref(a), stream))
+            info["buckets_reused"] = reuse
+        if cache_buckets and not reuse:
+            # keep the buckets only: the scratch of the sort (two thirds of the workspace) goes back to the allocator
+            keep = int(lib.srx_feature_overlap_bucket_bytes(C.byref(a)))
+            kept = torch.empty(keep, dtype=torch.uint8, device=dev)
+            kept.copy_(ws[:keep])
+            buckets[bkey] = kept
     return out
 
 

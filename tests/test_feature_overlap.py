@@ -67,6 +67,46 @@ def test_gpu_feature_overlap_vs_oracle_wide_channels(dtype, tol, case):
 
 
 @pytest.mark.gpu
+def test_gpu_feature_overlap_reuses_buckets_across_layers_and_steps():
+    """One id batch, three attention layers of two sizes and dtypes, two denoise steps: the bucketing pass runs once per
+    (size, key capacity) and every later call reads the cached buckets; `IDMap.invalidate()` drops them."""
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import IDMap
+    from stable_renderer_b200.feature import feature_overlap
+    F, H = 4, 128
+    ids = synthetic.make_ids(F, H, H, tex_h=64, tex_w=64, frac_2048=0.05, seed=62)
+    idm = IDMap(tensor=ids.cuda())
+    gen = torch.Generator().manual_seed(11)
+    seen = []
+    for step in range(2):
+        for hw, c, dtype, tol in ((256, 320, torch.float32, (2e-5, 5e-6)), (256, 640, torch.float16, (1e-2, 1e-2)),
+                                  (64, 1280, torch.float32, (2e-5, 5e-6))):
+            feats = torch.randn(F, hw, c, generator=gen).to(dtype)
+            info = {}
+            out = feature_overlap(feats.cuda(), idm, ratio=0.6, map_size=(H, H), key_capacity=64 * 64, info=info)
+            want = O.feature_overlap(feats.float().numpy(), ids.numpy(), ratio=0.6, map_height=H, map_width=H)
+            assert_close(t2n(out), want, tol[0], tol[1], f"step {step} hw {hw} c {c}")
+            assert info["rows_gathered"] >= F * hw
+            seen.append(info["buckets_reused"])
+    assert seen == [False, True, False, True, True, True]
+    assert len(idm._feature_buckets) == 2
+    # new content in the same tensor: without invalidate() the cached buckets would be stale
+    ids2 = synthetic.make_ids(F, H, H, tex_h=64, tex_w=64, frac_2048=0.05, seed=63)
+    idm.tensor.copy_(ids2.cuda())
+    idm.invalidate()
+    assert not idm._feature_buckets
+    feats = torch.randn(F, 256, 320, generator=gen)
+    info = {}
+    out = feature_overlap(feats.cuda(), idm, ratio=0.6, map_size=(H, H), key_capacity=64 * 64, info=info)
+    assert info["buckets_reused"] is False
+    assert_close(t2n(out), O.feature_overlap(feats.numpy(), ids2.numpy(), ratio=0.6, map_height=H, map_width=H), 2e-5, 5e-6, "after invalidate")
+    # cache_buckets=False keeps nothing
+    idm.invalidate()
+    feature_overlap(feats.cuda(), idm, ratio=0.6, map_size=(H, H), key_capacity=64 * 64, cache_buckets=False)
+    assert not idm._feature_buckets
+
+
+@pytest.mark.gpu
 def test_gpu_post_atten_inject_switch_and_errors():
     from stable_renderer_b200 import _lib, synthetic
     from stable_renderer_b200.corresponder import OverlapCorresponder

@@ -40,10 +40,18 @@ for h, c in ((64, 320), (32, 640), (16, 1280)):
     for dt in (torch.float16, torch.float32):
         g = torch.Generator(device="cpu").manual_seed(h * c)
         x = torch.randn(F, h * h, c, generator=g).to(dev, dt)
-        med, best = timed(lambda: feature_overlap(x, idm, 0.6, map_size=(H, H), key_capacity=512 * 512, check=False))
-        nbytes = ids.numel() * ids.element_size() + 2 * x.numel() * x.element_size()
-        print(f"feature_overlap F={F} ids {H}x{H} hw={h}x{h} c={c} {str(dt)[6:]}: median {med * 1e3:.1f} us, min {best * 1e3:.1f} us, "
-              f"{nbytes / 1e6:.1f} MB algorithmic -> {nbytes / med / 1e6:.0f} GB/s")
+        kw = dict(map_size=(H, H), key_capacity=512 * 512, check=False)
+        info = {}
+        feature_overlap(x, idm, 0.6, info=info, **kw)
+        row = c * x.element_size()
+        apply_bytes = (info["rows_gathered"] + 3 * F * h * h) * row
+        id_bytes = ids.numel() * ids.element_size()
+        med_b, best_b = timed(lambda: feature_overlap(x, idm, 0.6, cache_buckets=False, **kw))
+        med, best = timed(lambda: feature_overlap(x, idm, 0.6, **kw))
+        print(f"feature_overlap F={F} ids {H}x{H} hw={h}x{h} c={c} {str(dt)[6:]}: rows gathered {info['rows_gathered']} "
+              f"({info['rows_gathered'] * row / 1e6:.0f} MB through L2) | buckets cached: median {med * 1e3:.1f} us, min {best * 1e3:.1f} us, "
+              f"{apply_bytes / 1e6:.0f} MB algorithmic -> {apply_bytes / med / 1e6:.0f} GB/s | bucketing every call: median "
+              f"{med_b * 1e3:.1f} us ({(apply_bytes + id_bytes) / 1e6:.0f} MB -> {(apply_bytes + id_bytes) / med_b / 1e6:.0f} GB/s)")
 
 # cell-similarity overlap: b frames of a 64x64 id crop (4096 pixels), 8x8 cells, c = 320
 b, P, cells, c = 16, 64 * 64, 64, 320
