@@ -336,8 +336,13 @@ def run_overlap(args, workload: str, rank: int, local: int, world: int, light: b
         one_step(i)
     if graphs:
         graphs[0].replay()                              # graph warm-up (first replay uploads the graph)
-    barrier(world)
     sampler.start()
+    barrier(world)
+    # Two more untimed steps right in front of the start event: at N > 1 the step kernel is itself a rendezvous of all ranks, so
+    # every rank's start event fires within microseconds of the others' on the device — without them the ranks' host-side skew
+    # after the barrier (hundreds of microseconds) lands inside a timed region that is only K x 0.1 ms long.
+    for i in range(2):
+        one_step(i)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     run_k_steps()
@@ -417,6 +422,8 @@ def run_overlap(args, workload: str, rank: int, local: int, world: int, light: b
 
         run_jobs(True)                                  # warm-up (also sizes the pools)
         barrier(world)
+        for _ in range(2):                              # device-side alignment of the ranks, as above
+            plans[0].step(xs_j[0], RATIO, cached=True)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         run_jobs(False)

@@ -58,6 +58,9 @@ def test_our_arm_line():
     x = d["extra"]
     assert x["cfg2"]["config"]["workload"].startswith("cfg2") and x["cfg2"]["cached_plan"]["job"]["steps"] == 20
     assert x["cfg4_bake"]["unit"] == "views/s" and x["cfg4_bake_reference_modes"]["value"] > 0
+    fo = x["feature_overlap"]["sizes"]
+    assert set(fo) == {"hw64x64_c320", "hw32x32_c640", "hw16x16_c1280"}
+    assert all(0 < v["ms_per_call"] < v["ms_per_call_bucketing_every_call"] and v["rows_gathered"] > 0 for v in fo.values())
 
 
 def test_workload_string_is_shared_by_both_arms():
