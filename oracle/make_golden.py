@@ -251,32 +251,41 @@ def randn_init_cases(R):
     save("randn_init", t=t.numpy(), expanded=exp.numpy(), unique=uniq.numpy(), inverse=inv.numpy().astype(np.int32),
          table=table.numpy(), seed=np.int64(11))
 
+    # CreateNoiseSequenceFromIdMap: the reference's own __call__ body (ref_shim.noise_node_call), on CPU
+    import hashlib
     from stable_renderer_b200 import synthetic
     corrmap = R["corrmap"]
+    node_call = ref_shim.noise_node_call()
     size, F, seed = 512, 1, 77
     ids = synthetic.make_ids(F, size, size, tex_h=96, tex_w=96, frac_2048=0.05, seed=17)
     out = {}
     for option in ("nearest", "mean", "max", "min"):
-        idm = corrmap.IDMap(tensor=ids.clone())
-        latent_generator = torch.manual_seed(seed)
-        noise_generator = torch.manual_seed(seed + 1)
-        latent = torch.randn([1, 4, size, size], device="cpu", generator=latent_generator).repeat(F, 1, 1, 1)
-        noise = torch.randn([1, 4, size, size], device="cpu", generator=noise_generator).repeat(F, 1, 1, 1)
         with ref_shim.quiet():
-            vsi = idm.create_vertex_screen_info()
-        xs, ys, fs = (vsi[:, 4] * size).long(), (vsi[:, 5] * size).long(), vsi[:, 6].long()
-        for tensor in (latent, noise):
-            tab = torch.cat([tensor[fs, :, ys, xs], vsi[:, 3].unsqueeze(-1)], dim=-1)
-            rnd, _ = mu.tensor_group_by_then_randn_init(tab, index_column=-1, value_columns=[0, 1, 2, 3], return_unique=True)
-            tensor[fs, :, ys, xs] = rnd
+            res = node_call(None, corrmap.IDMap(tensor=ids.clone()), seed, "SD15", option)
         if option == "nearest":
-            out["nearest_samples"] = Fnn.interpolate(latent, size=(size // 8, size // 8), mode="nearest").numpy()
-            out["nearest_noise"] = Fnn.interpolate(noise, size=(size // 8, size // 8), mode="nearest").numpy()
+            out["nearest_samples"], out["nearest_noise"] = res["samples"].numpy(), res["noise"].numpy()
         else:
-            v = noise.view(-1, 4, 8, 8)
-            v = {"mean": lambda a: a.mean(dim=(1, 2)), "max": lambda a: a.amax(dim=(1, 2)), "min": lambda a: a.amin(dim=(1, 2))}[option](v)
-            out[option + "_noise"] = v.view(-1, 4, size // 8, size // 8).numpy()
+            assert not res["samples"].any()
+            out[option + "_noise"] = res["noise"].numpy()
     save("noise_from_idmap", seed=np.int64(seed), id_seed=np.int64(17), tex=np.int64(96), size=np.int64(size), frames=np.int64(F), **out)
+
+    # id maps of another size than the node's working size, permuted / shared latent frames: digest + every 61st value of the
+    # reference node's outputs (the full tensors are megabytes of random floats)
+    more = {}
+    names = []
+    for case, (H, fi) in {"map_1024_on_sd15": (1024, [0, 1]), "map_256_on_sd15": (256, [1, 0]), "map_384_on_sd15": (384, [0, 1]),
+                          "two_id_frames_one_latent_frame": (512, [0, 0, 2]), "permuted_frames": (512, [2, 0, 1])}.items():
+        ids_c = synthetic.make_ids(len(fi), H, H, tex_h=150, tex_w=150, frac_2048=0.1, seed=9)
+        names.append(f"{case}:{H}:{','.join(map(str, fi))}")
+        for option in ("nearest", "max", "mean"):
+            with ref_shim.quiet():
+                res = node_call(None, corrmap.IDMap(tensor=ids_c.clone(), frame_indices=list(fi)), 321, "SD15", option)
+            for k in (("samples", "noise") if option == "nearest" else ("noise",)):
+                arr = np.ascontiguousarray(res[k].numpy())
+                more[f"{case}_{option}_{k}_shape"] = np.array(arr.shape, dtype=np.int64)
+                more[f"{case}_{option}_{k}_every61"] = arr.reshape(-1)[::61].copy()
+                more[f"{case}_{option}_{k}_sha256"] = np.array(hashlib.sha256(arr.tobytes()).hexdigest())
+    save("noise_node_other_sizes", cases=np.array(names), seed=np.int64(321), id_seed=np.int64(9), tex=np.int64(150), **more)
 
 
 def dump_cases(R):
@@ -344,46 +353,44 @@ def _gbuffer_attachments(g, H, W, coverage):
     return dict(color=color, ids=ids, pos=pos, normal_depth=nd, noise=noise, canny=canny)
 
 
+class _FboTex:
+    """Stand-in for a G-buffer `Texture`: holds the attachment in GL row order; `tensor(update, flip)` is texture.py:221-254 for a
+    CPU tensor (the flip is the only arithmetic of that method)."""
+
+    def __init__(self, data=None):
+        self.data = data
+
+    def tensor(self, update=True, flip=True):
+        return self.data.flip(0) if flip else self.data
+
+
+class _Ns:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
 def ingest_cases(R):
-    """RenderManager._save_frame_data (renderManager.py:877-948) and the closer-pixel merge (:121-133).  RenderManager cannot
-    be imported (OpenGL, window, managers), so the two bodies are replayed statement by statement on CPU tensors around the
-    reference's REAL adaptive_instance_normalization; `Texture.tensor(update=True, flip=True)` becomes `.flip(0)` of the
-    GL-order attachment (texture.py:236,253)."""
-    ain = R["math_utils"].adaptive_instance_normalization
+    """RenderManager._save_frame_data (renderManager.py:877-948) and the closer-pixel merge inside _wrapIdenticalGBufferTask
+    (:88-133): the reference's OWN function bodies (ref_shim.render_manager_functions cuts them out of the file; the module cannot
+    be imported — OpenGL, window, managers) run against stand-ins for the manager and its seven textures."""
+    save_frame_data, wrap_task = ref_shim.render_manager_functions()
     g = torch.Generator().manual_seed(2024)
     H, W = 48, 64
     bg = torch.randn((1, H, W, 4), generator=g, dtype=torch.float32)
-    data = {}
+    tex_names = dict(color="colorFBOTex", ids="idFBOTex", pos="posFBOTex", normal_depth="normal_and_depth_FBOTex",
+                     noise="noiseFBOTex", canny="cannyFBOTex")
+    rm = _Ns(data_to_be_added_to_engineData={}, GlobalBGNoise=bg, engine=_Ns(RuntimeManager=_Ns(FrameCount=0)),
+             **{v: _FboTex() for v in tex_names.values()})
     src_all = []
     for frame in range(2):
         src = _gbuffer_attachments(g, H, W, 0.55)
         src_all.append(src)
-        tex = {k: v.flip(0) for k, v in src.items()}                                          # Texture.tensor(flip=True)
-
-        def cat(key, val):
-            data[key] = val if key not in data else torch.cat([data[key], val], dim=0)
-        color_data = tex["color"].clone().unsqueeze(0)
-        mask_data = 1.0 - color_data[..., 3].squeeze(-1)
-        color_data = color_data[..., :3]
-        cat("color_maps", color_data)
-        cat("masks", mask_data)
-        cat("id_maps", tex["ids"].clone().unsqueeze(0))
-        cat("pos_maps", tex["pos"].clone().unsqueeze(0))
-        nd = tex["normal_depth"].clone().unsqueeze(0)
-        normal_data = nd[..., :3]
-        depth_data = nd[..., 3].unsqueeze(-1)
-        depth_data = torch.cat([depth_data, ] * 3, dim=-1)
-        cat("normal_maps", normal_data)
-        cat("depth_maps", depth_data)
-        noise = tex["noise"].clone().unsqueeze(0)
-        mask = mask_data.unsqueeze(-1).expand_as(noise).to(device=noise.device)
-        noise = noise * (1.0 - mask) + bg * mask
-        height, width = noise.shape[1], noise.shape[2]
-        noise = noise.view(-1, 8, 8, 4).mean(dim=(1, 2)).view(height // 8, width // 8, 4)
-        noise = ain(noise.unsqueeze(0), tex["noise"].unsqueeze(0), mode='NHWC')
-        noise = noise.contiguous()
-        cat("noise_maps", noise)
-        cat("canny_maps", tex["canny"].clone().unsqueeze(0))
+        for k, v in src.items():
+            getattr(rm, tex_names[k]).data = v
+        rm.engine.RuntimeManager.FrameCount = frame
+        save_frame_data(rm)
+    data = rm.data_to_be_added_to_engineData
+    assert data.pop("frame_indices") == [0, 1]
     out = {"bg_noise": bg.numpy()}
     for f, src in enumerate(src_all):
         for k, v in src.items():
@@ -391,11 +398,17 @@ def ingest_cases(R):
     for k, v in data.items():
         out[k] = v.numpy().view(np.uint16) if v.dtype == torch.float16 else v.numpy()
 
-    # closer-pixel merge of three draws (renderManager.py:121-133 with the buffers of :219-357)
-    temp = dict(color=torch.zeros(H, W, 4, dtype=torch.float16), ids=torch.zeros(H, W, 4, dtype=torch.int32),
-                pos=torch.zeros(H, W, 3), normal=torch.zeros(H, W, 3, dtype=torch.float16),
-                depth=torch.zeros(H, W, dtype=torch.float16), noise=torch.zeros(H, W, 4, dtype=torch.float16),
-                canny=torch.zeros(H, W, 3, dtype=torch.float16))
+    # closer-pixel merge of three draws with the temp buffers of renderManager.py:219-357
+    rm._color_buffer_temp = torch.zeros(H, W, 4, dtype=torch.float16)
+    rm._id_buffer_temp = torch.zeros(H, W, 4, dtype=torch.int32)
+    rm._pos_buffer_temp = torch.zeros(H, W, 3)
+    rm._normal_buffer_temp = torch.zeros(H, W, 3, dtype=torch.float16)
+    rm._depth_buffer_temp = torch.zeros(H, W, dtype=torch.float16)
+    rm._noise_buffer_temp = torch.zeros(H, W, 4, dtype=torch.float16)
+    rm._canny_buffer_temp = torch.zeros(H, W, 3, dtype=torch.float16)
+    rm.BindGBufferTexToShader = lambda shader: None
+    rm._update_gbuffer_tex_to_shader_binding_tex = lambda: None
+    shader = _Ns(useProgram=lambda: None)
     for d in range(3):
         src = _gbuffer_attachments(g, H, W, 0.4)
         if d == 2:
@@ -403,19 +416,16 @@ def ingest_cases(R):
         src_prev = src
         for k, v in src.items():
             out[f"draw{d}_{k}"] = v.numpy().view(np.uint16) if v.dtype == torch.float16 else v.numpy()
-        cur = src["normal_depth"].flip(0)
-        current_depth = cur[..., -1].squeeze()
-        current_normal = cur[..., :-1]
-        closer = current_depth > temp["depth"]
-        temp["depth"][closer] = current_depth[closer]
-        temp["normal"][closer] = current_normal[closer]
-        temp["color"][closer] = src["color"].flip(0)[closer]
-        temp["ids"][closer] = src["ids"].flip(0)[closer]
-        temp["pos"][closer] = src["pos"].flip(0)[closer]
-        temp["noise"][closer] = src["noise"].flip(0)[closer]
-        temp["canny"][closer] = src["canny"].flip(0)[closer]
+
+        def draw(src=src):                                                                    # the "task": the draw fills the attachments
+            for k, v in src.items():
+                getattr(rm, tex_names[k]).data = v
+        wrap_task(rm, draw, shader, None, None, True)
+    temp = dict(color=rm._color_buffer_temp, ids=rm._id_buffer_temp, pos=rm._pos_buffer_temp, normal=rm._normal_buffer_temp,
+                depth=rm._depth_buffer_temp, noise=rm._noise_buffer_temp, canny=rm._canny_buffer_temp)
     for k, v in temp.items():
         out[f"temp_{k}"] = v.numpy().view(np.uint16) if v.dtype == torch.float16 else v.numpy()
+    out["generator"] = np.array("RenderManager._save_frame_data and _wrapIdenticalGBufferTask bodies of the reference, unmodified, on stand-in textures")
     save("frame_ingest", **out)
 
 
@@ -559,6 +569,10 @@ def main():
     if "--only-ingest" in sys.argv:
         torch.set_num_threads(1)
         ingest_cases(ref_shim.load_reference())
+        return
+    if "--only-randn" in sys.argv:
+        torch.set_num_threads(1)
+        randn_init_cases(ref_shim.load_reference())
         return
     if "--only-latent-init" in sys.argv:
         torch.set_num_threads(1)

@@ -329,6 +329,80 @@ def post_atten_inject_body():
     raise KeyError("post_atten_inject")
 
 
+def render_manager_functions():
+    """``RenderManager._save_frame_data`` (renderManager.py:877-948) and ``_wrapIdenticalGBufferTask`` (:88-133), cut out of
+    the reference's file and compiled unmodified except that parameter annotations are dropped (they name engine classes).  The
+    module itself cannot be imported (OpenGL context, window, managers): the two functions run against duck-typed stand-ins for the
+    manager and its textures — see oracle/make_golden.py::ingest_cases.  Returns ``(save_frame_data(self), wrap_task(render_manager,
+    task, shader, mesh, callback=None, save_to_temp=False))``."""
+    import ast
+    R = load_reference()
+    path = os.path.join(REFERENCE_ROOT, "source/engine/managers/renderManager.py")
+    with open(path) as f:
+        tree = ast.parse(f.read())
+
+    def strip(fn):
+        fn.returns = None
+        for a in fn.args.args + fn.args.kwonlyargs:
+            a.annotation = None
+        return fn
+    found = {}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "_wrapIdenticalGBufferTask":
+            found["wrap"] = strip(node)
+        if isinstance(node, ast.ClassDef) and node.name == "RenderManager":
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == "_save_frame_data":
+                    found["save"] = strip(fn)
+    assert set(found) == {"wrap", "save"}, found.keys()
+    import torch
+    gl = _StubModule("OpenGL.GL")
+    gl.glClear = lambda *a, **k: None
+    gl.glDisable = gl.glEnable = lambda *a, **k: None
+    gl.GL_DEPTH_BUFFER_BIT, gl.GL_COLOR_BUFFER_BIT, gl.GL_CULL_FACE = 0x100, 0x4000, 0x0B44
+    ns = {"torch": torch, "gl": gl, "adaptive_instance_normalization": R["math_utils"].adaptive_instance_normalization}
+    mod = ast.Module(body=[found["wrap"], found["save"]], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    exec(compile(mod, path, "exec"), ns)
+    return ns["_save_frame_data"], ns["_wrapIdenticalGBufferTask"]
+
+
+def noise_node_call():
+    """``CreateNoiseSequenceFromIdMap.__call__`` (source/comfyUI/stable_rendering/_nodes/loaders.py:154-271), cut out of the
+    reference's file: parameter annotations dropped (ComfyUI type constructors) and the device string ``'cuda'`` replaced by
+    ``'cpu'`` (five ``.to('cuda')`` calls — the build container has no GPU); every other statement runs as written, around the
+    reference's real ``tensor_group_by_then_randn_init`` and ``IDMap``.  Returns ``f(self, id_map, seed, sd_version, downsample_option)``
+    whose result is a dict with ``samples`` and ``noise``."""
+    import ast
+    import torch
+    import torch.nn.functional as F
+    R = load_reference()
+    path = os.path.join(REFERENCE_ROOT, "source/comfyUI/stable_rendering/_nodes/loaders.py")
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == "CreateNoiseSequenceFromIdMap":
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == "__call__":
+                    fn.returns = None
+                    for a in fn.args.args:
+                        a.annotation = None
+                    swapped = 0
+                    for sub in ast.walk(fn):
+                        if isinstance(sub, ast.Constant) and sub.value == "cuda":
+                            sub.value = "cpu"
+                            swapped += 1
+                    assert swapped >= 3, swapped
+                    fn.name = "noise_node_call"
+                    mod = ast.Module(body=[fn], type_ignores=[])
+                    ast.fix_missing_locations(mod)
+                    ns = {"torch": torch, "F": F, "LATENT": lambda **kw: dict(kw),
+                          "tensor_group_by_then_randn_init": R["math_utils"].tensor_group_by_then_randn_init}
+                    exec(compile(mod, path, "exec"), ns)
+                    return ns["noise_node_call"]
+    raise KeyError("CreateNoiseSequenceFromIdMap.__call__")
+
+
 def taichi_cells_overlap_python():
     """``taichi_cells_overlap`` (corr_utils.py:110-134) executed as plain Python: the shim's taichi stand-in makes
     ``ti.kernel`` / ``ti.func`` identity decorators, so only ``ti.ndrange`` and ``ti.math.ivec2`` need real behaviour."""

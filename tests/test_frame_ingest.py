@@ -1,5 +1,6 @@
 """Frame ingest (`RenderManager._save_frame_data`, renderManager.py:877-948) and the closer-pixel merge (:121-133) against a
-fixture replayed around the reference's real AdaIN (oracle/make_golden.py::ingest_cases)."""
+fixture produced by the reference's own function bodies on stand-in textures (oracle/make_golden.py::ingest_cases,
+oracle/ref_shim.py::render_manager_functions)."""
 import os
 
 import numpy as np
@@ -19,7 +20,7 @@ def _att(g, prefix):
     return {k: (g[f"{prefix}_{k}"].view(np.float16) if k in HALF_KEYS else g[f"{prefix}_{k}"]) for k in ATT}
 
 
-def test_oracle_frame_ingest_matches_reference_replay():
+def test_oracle_frame_ingest_matches_reference_body():
     g = np.load(GOLD)
     for f in range(2):
         out = O.frame_ingest(bg_noise=g["bg_noise"][0], flip=True, **_att(g, f"src{f}"))
@@ -30,7 +31,7 @@ def test_oracle_frame_ingest_matches_reference_replay():
         assert np.allclose(out["noise_maps"], g["noise_maps"][f], rtol=2e-5, atol=2e-5)
 
 
-def test_oracle_merge_closer_matches_reference_replay():
+def test_oracle_merge_closer_matches_reference_body():
     g = np.load(GOLD)
     H, W = g["temp_depth"].shape
     temp = dict(color=np.zeros((H, W, 4), np.float16), ids=np.zeros((H, W, 4), np.int32), pos=np.zeros((H, W, 3), np.float32),

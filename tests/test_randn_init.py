@@ -48,6 +48,57 @@ def test_oracle_noise_sequence_matches_reference(golden):
     np.testing.assert_allclose(n, g["mean_noise"], rtol=1e-6, atol=1e-7)
 
 
+def _other_cases(g):
+    for entry in g["cases"]:
+        case, H, fi = str(entry).split(":")
+        yield case, int(H), [int(v) for v in fi.split(",")]
+
+
+def _check_against_node_fixture(g, case, option, key, arr):
+    """Fixture = digest + every 61st value of the reference node's output (oracle/make_golden.py::randn_init_cases)."""
+    import hashlib
+    arr = np.ascontiguousarray(arr)
+    assert tuple(g[f"{case}_{option}_{key}_shape"]) == arr.shape, (case, option, key)
+    if option == "mean":                                  # float sums in another order
+        np.testing.assert_allclose(arr.reshape(-1)[::61], g[f"{case}_{option}_{key}_every61"], rtol=1e-6, atol=1e-7)
+    else:
+        assert np.array_equal(arr.reshape(-1)[::61], g[f"{case}_{option}_{key}_every61"]), (case, option, key)
+        assert hashlib.sha256(arr.tobytes()).hexdigest() == str(g[f"{case}_{option}_{key}_sha256"]), (case, option, key)
+
+
+def test_oracle_noise_sequence_other_sizes_matches_reference_node(golden):
+    """Id maps of another size than the working size (1024 / 256 / 384 on SD15), two id frames on one latent frame, permuted
+    frames: the oracle against the reference node's own __call__ body, bit for bit (digests of the full outputs)."""
+    from stable_renderer_b200 import synthetic
+    g = golden("noise_node_other_sizes")
+    size, seed = 512, int(g["seed"])
+    for case, H, fi in _other_cases(g):
+        ids = synthetic.make_ids(len(fi), H, H, tex_h=int(g["tex"]), tex_w=int(g["tex"]), frac_2048=0.1, seed=int(g["id_seed"])).numpy()
+        n_unique = len(np.unique(O.vertex_screen_info(ids, fi)[:, 3]))
+        bl, bn, kl, kn = _node_draws(seed, size, n_unique)
+        for option in ("nearest", "max", "mean"):
+            s_, n_ = O.noise_sequence_from_ids(ids, fi, bl, bn, kl, kn, size, option)
+            _check_against_node_fixture(g, case, option, "noise", n_)
+            if option == "nearest":
+                _check_against_node_fixture(g, case, option, "samples", s_)
+
+
+@pytest.mark.gpu
+def test_gpu_noise_sequence_other_sizes_matches_reference_node(golden):
+    from stable_renderer_b200 import synthetic
+    from stable_renderer_b200.corrmap import IDMap
+    from stable_renderer_b200.loaders import CreateNoiseSequenceFromIdMap
+    g = golden("noise_node_other_sizes")
+    for case, H, fi in _other_cases(g):
+        ids = synthetic.make_ids(len(fi), H, H, tex_h=int(g["tex"]), tex_w=int(g["tex"]), frac_2048=0.1, seed=int(g["id_seed"]))
+        idm = IDMap(tensor=ids.cuda(), frame_indices=fi)
+        for option in ("nearest", "max", "mean"):
+            out = CreateNoiseSequenceFromIdMap()(idm, int(g["seed"]), "SD15", option, rng_device="cpu")
+            _check_against_node_fixture(g, case, option, "noise", out["noise"].cpu().numpy())
+            if option == "nearest":
+                _check_against_node_fixture(g, case, option, "samples", out["samples"].cpu().numpy())
+
+
 @pytest.mark.gpu
 def test_gpu_randn_init_matches_reference_grouping(golden):
     from stable_renderer_b200.math_utils import tensor_group_by_then_randn_init
