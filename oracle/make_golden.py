@@ -150,6 +150,11 @@ def legacy_cases(R):
             np.save(os.path.join(iddir, f"id_{f}.npy"), ids[f].numpy())
         with ref_shim.quiet():
             cmap = CorrespondenceMap.FromExisting(iddir, enable_cache=False)
+        # FromExisting pickles the map beside the id directory (correspondence_map.py:170-172): that file, as written by the
+        # reference's own save_cache, is the fixture for the cache loader
+        with open(os.path.join(td, "corr_map.pkl"), "rb") as fsrc, open(os.path.join(OUT, "legacy_corr_map.pkl"), "wb") as fdst:
+            fdst.write(fsrc.read())
+        print(f"legacy_corr_map.pkl: {os.path.getsize(os.path.join(OUT, 'legacy_corr_map.pkl')) / 1024:.1f} KiB")
     keys = np.array(list(cmap.Map.keys()), dtype=np.int64)
     lens = np.array([len(v) for v in cmap.Map.values()], dtype=np.int64)
     flat = np.array([(p[0], p[1], f) for v in cmap.Map.values() for (p, f) in v], dtype=np.int64)
@@ -573,6 +578,10 @@ def main():
     if "--only-randn" in sys.argv:
         torch.set_num_threads(1)
         randn_init_cases(ref_shim.load_reference())
+        return
+    if "--only-legacy" in sys.argv:
+        torch.set_num_threads(1)
+        legacy_cases(ref_shim.load_reference())
         return
     if "--only-latent-init" in sys.argv:
         torch.set_num_threads(1)

@@ -152,17 +152,59 @@ class CorrespondenceMap:
             pickle.dump({"ids": self._ids.cpu(), "merge_len": self._merge_len}, f)
 
     @classmethod
-    def LoadFromCache(cls, path: str) -> "CorrespondenceMap":
-        """`LoadFromCache` (correspondence_map.py:177-192)."""
+    def LoadFromCache(cls, path: str, device=None) -> "CorrespondenceMap":
+        """`LoadFromCache` (correspondence_map.py:177-192).  Reads this package's cache (the id buffers) and the REFERENCE's
+        `corr_map.pkl` — a pickle of its dict-based `CorrespondenceMap` object (`save_cache`, :194-205): the dict
+        {id tuple: [([row, col], frame), ...]} is turned back into `[F,H,W,4]` id buffers with array operations, so the plan
+        builder is fed without the reference's Python triple loop (:148-168).  Only builtins and numpy scalars / arrays are
+        unpickled; the reference class is mapped by name onto an attribute holder (no reference code runs).  A map that was merged
+        before it was cached (`merge_nearby`) keeps its merged keys; its entries are then ordered by position, not by sub-trace."""
         import pickle
         path = str(path)
         if os.path.exists(path) and os.path.isdir(path):
             path = os.path.join(path, "corr_map.pkl")
         if not os.path.exists(path):
             raise FileNotFoundError(f"Correspondence map cache file not found at {path}")
+
+        class _Holder:                                   # stands in for the pickled reference object
+            pass
+
+        class _Restricted(pickle.Unpickler):
+            def find_class(self, module, name):
+                if name == "CorrespondenceMap":
+                    return _Holder
+                root = module.split(".")[0]
+                if root in ("builtins", "collections", "numpy", "torch", "_codecs", "copyreg"):
+                    return super().find_class(module, name)
+                raise pickle.UnpicklingError(f"refusing to unpickle {module}.{name}")
         with open(path, "rb") as f:
-            d = pickle.load(f)
-        return cls(d["ids"], merge_len=d["merge_len"])
+            d = _Restricted(f).load()
+        if isinstance(d, dict) and "ids" in d:
+            ids = d["ids"] if device is None else d["ids"].to(device)
+            return cls(ids, merge_len=d["merge_len"])
+        if not isinstance(d, _Holder) or not isinstance(getattr(d, "_correspondence_map", None), dict):
+            raise ValueError(f"{path} holds neither this package's cache nor a pickled reference CorrespondenceMap")
+        m = d._correspondence_map
+        if not m:
+            raise ValueError(f"{path}: empty correspondence map")
+        keys = np.array([[int(c) for c in k] for k in m.keys()], dtype=np.int64)
+        if keys.ndim != 2 or keys.shape[1] != 4:
+            raise ValueError(f"{path}: id keys must be 4-tuples, got shape {keys.shape}")
+        lens = np.fromiter((len(v) for v in m.values()), dtype=np.int64, count=len(m))
+        flat = np.array([(p[0], p[1], f) for v in m.values() for (p, f) in v], dtype=np.int64).reshape(-1, 3)
+        W, H, F = getattr(d, "_width", None), getattr(d, "_height", None), getattr(d, "_num_frames", None)
+        H = int(H) if H else int(flat[:, 0].max()) + 1
+        W = int(W) if W else int(flat[:, 1].max()) + 1
+        F = int(F) if F else int(flat[:, 2].max()) + 1
+        if flat.min() < 0 or flat[:, 0].max() >= H or flat[:, 1].max() >= W or flat[:, 2].max() >= F:
+            raise ValueError(f"{path}: pixel positions outside the {F} x {H} x {W} id buffers (a position callback was used)")
+        lo, hi = np.iinfo(np.int32).min, np.iinfo(np.int32).max
+        if keys.min() < lo or keys.max() > hi:
+            raise ValueError(f"{path}: id components outside int32")
+        ids = np.zeros((F, H, W, 4), dtype=np.int32)
+        ids[flat[:, 2], flat[:, 0], flat[:, 1]] = np.repeat(keys, lens, axis=0).astype(np.int32)
+        t = torch.from_numpy(ids)
+        return cls(t if device is None else t.to(device), num_frames=F)
 
     # -- construction ---------------------------------------------------------------------------------------------------
     @classmethod
@@ -170,10 +212,24 @@ class CorrespondenceMap:
         return cls(ids, merge_len=merge_len, num_frames=num_frames)
 
     @classmethod
-    def FromExisting(cls, directory: str, num_frames: Optional[int] = None, device=None, **_ignored) -> "CorrespondenceMap":
+    def FromExisting(cls, directory: str, num_frames: Optional[int] = None, device=None, enable_cache: bool = True,
+                     **_ignored) -> "CorrespondenceMap":
         """Loads the `*.npy` id dumps of a directory ordered by the first number in each file name
-        (correspondence_map.py:122-143).  The reference's pickle cache and position callback do not apply."""
+        (correspondence_map.py:122-143).  With `enable_cache` an existing `corr_map.pkl` — this package's or the reference's —
+        is used instead, looked for where the reference looks (:103-116): the path itself, the directory, the parent of an `id`
+        directory.  No cache is written (building from the dumps is one `np.stack`); the position callback does not apply."""
         directory = str(directory)
+        if enable_cache:
+            cache_path = None
+            if os.path.isfile(directory) and directory.endswith(".pkl"):
+                cache_path = directory
+            elif os.path.isdir(directory) and "corr_map.pkl" in os.listdir(directory):
+                cache_path = os.path.join(directory, "corr_map.pkl")
+            elif os.path.isdir(directory) and directory.rstrip("/\\").endswith("id") and \
+                    os.path.isfile(os.path.join(directory, "..", "corr_map.pkl")):
+                cache_path = os.path.join(directory, "..", "corr_map.pkl")
+            if cache_path is not None:
+                return cls.LoadFromCache(cache_path, device=device)
         assert os.path.isdir(directory), f"{directory} is not a directory"
         if not directory.endswith("id") and "id" in os.listdir(directory):
             directory = os.path.join(directory, "id")

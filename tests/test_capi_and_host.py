@@ -119,6 +119,45 @@ def test_correspondence_map_from_directory(tmp_path, golden):
     assert idm2.frame_indices == [1, 2] and np.array_equal(idm2.tensor.numpy(), g["ids"][1:3])
 
 
+def test_reference_corr_map_pkl_loads_into_id_buffers(golden, tmp_path):
+    """`corr_map.pkl` as written by the reference's own `save_cache` (fixture: oracle/make_golden.py::legacy_cases) -> id buffers,
+    same dict in the same order; the unpickler runs no reference code and refuses anything but builtins / numpy."""
+    import pickle
+    import shutil
+    from stable_renderer_b200.overlap import CorrespondenceMap
+    g = golden("legacy_corrmap")
+    src = os.path.join(os.path.dirname(__file__), "golden", "legacy_corr_map.pkl")
+    cm = CorrespondenceMap.LoadFromCache(src)
+    assert np.array_equal(cm.ids.numpy(), g["ids"].astype(np.int32))
+    assert cm.num_frames == g["ids"].shape[0] and (cm.width, cm.height) == tuple(g["size"])
+    m = cm.Map
+    assert np.array_equal(np.array(list(m.keys())), g["keys"])
+    assert np.array_equal(np.array([(p[0], p[1], f) for v in m.values() for (p, f) in v]), g["traces"])
+    shutil.copy(src, tmp_path / "corr_map.pkl")                         # a directory holding the cache
+    assert len(CorrespondenceMap.LoadFromCache(str(tmp_path))) == len(g["keys"])
+    (tmp_path / "id").mkdir()                                           # FromExisting finds it like the reference does
+    for where in (str(tmp_path), str(tmp_path / "id"), str(tmp_path / "corr_map.pkl")):
+        assert np.array_equal(CorrespondenceMap.FromExisting(where).ids.numpy(), cm.ids.numpy())
+    with pytest.raises(FileNotFoundError):
+        CorrespondenceMap.FromExisting(str(tmp_path / "id"), enable_cache=False)     # no id dumps there
+    cm.save_cache(str(tmp_path / "own.pkl"))                            # this package's own cache format
+    assert np.array_equal(CorrespondenceMap.LoadFromCache(str(tmp_path / "own.pkl")).ids.numpy(), cm.ids.numpy())
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("true",))
+    with open(tmp_path / "evil.pkl", "wb") as f:
+        pickle.dump(Evil(), f)
+    with pytest.raises(pickle.UnpicklingError):
+        CorrespondenceMap.LoadFromCache(str(tmp_path / "evil.pkl"))
+    with open(tmp_path / "other.pkl", "wb") as f:
+        pickle.dump([1, 2, 3], f)
+    with pytest.raises(ValueError):
+        CorrespondenceMap.LoadFromCache(str(tmp_path / "other.pkl"))
+    with pytest.raises(FileNotFoundError):
+        CorrespondenceMap.LoadFromCache(str(tmp_path / "missing.pkl"))
+
+
 def test_idmap_masks_and_shapes(golden):
     from stable_renderer_b200.corrmap import IDMap
     g = golden("step_sq64_r8")
