@@ -319,11 +319,12 @@ __global__ void __launch_bounds__(FO_THREADS) k_fo_style(const XT *__restrict__ 
 // a ring per warp 185 us — about one row per 50 ns and SM whatever the structure; see profiles/r2_feature_overlap.txt.)
 // Statistics are summed over the warp's cells in float and folded over the CTA in double.
 #define FOW_WARPS 4
-#define FOW_CELLS 8
+#define FOW_CELLS 8                // cells per warp (default; SRX_FO_CELLS = 1..FOW_MAX_CELLS)
+#define FOW_MAX_CELLS 16
 template <typename XT, int P>
 __global__ void __launch_bounds__(FOW_WARPS * 32) k_fo_style_warp(const XT *__restrict__ feat, FoGeom g, const int4 *__restrict__ cellseg,
                                                                    const unsigned long long *__restrict__ pairs, const int *__restrict__ mult,
-                                                                   float ratio, float one_minus,
+                                                                   float ratio, float one_minus, int cpw,
                                                                    double *__restrict__ stats, unsigned long long *__restrict__ rows_out) {
     constexpr int VEC = FoVec<XT>::N;
     constexpr int UN = P <= 2 ? 4 : 2;
@@ -332,11 +333,11 @@ __global__ void __launch_bounds__(FOW_WARPS * 32) k_fo_style_warp(const XT *__re
     const int row_vecs = (g.c * (int)sizeof(XT)) >> 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hw = g.h * g.w;
-    const int per_cta = FOW_WARPS * FOW_CELLS;
+    const int per_cta = FOW_WARPS * cpw;
     const int ctas_per_frame = (hw + per_cta - 1) / per_cta;
     const int b = blockIdx.x / ctas_per_frame;
-    const int wc0 = (blockIdx.x - b * ctas_per_frame) * per_cta + warp * FOW_CELLS;
-    const int ncell = max(0, min(FOW_CELLS, hw - wc0));
+    const int wc0 = (blockIdx.x - b * ctas_per_frame) * per_cta + warp * cpw;
+    const int ncell = max(0, min(cpw, hw - wc0));
     const unsigned long long src_mask = (1ull << g.sb) - 1ull;
     // lane q < ncell holds cell q's segment; rows are numbered 0..total-1 across the cells (pair rows, then the cell's own row)
     int4 seg = make_int4(0, 0, 0, 0);
@@ -344,13 +345,13 @@ __global__ void __launch_bounds__(FOW_WARPS * 32) k_fo_style_warp(const XT *__re
     const int len = lane < ncell ? seg.y - seg.x + 1 : 0;
     int first = len;
 #pragma unroll
-    for (int d = 1; d < FOW_CELLS; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, first, d); if (lane >= d) first += t; }
-    const int total = __shfl_sync(0xffffffffu, first, FOW_CELLS - 1);
+    for (int d = 1; d < FOW_MAX_CELLS; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, first, d); if (lane >= d) first += t; }
+    const int total = __shfl_sync(0xffffffffu, first, FOW_MAX_CELLS - 1);
     first -= len;
     auto resolve = [&](int r, unsigned &row, float &m, int &meta) {
         int q = 0;
 #pragma unroll
-        for (int k = 1; k < FOW_CELLS; ++k) { const int fk = __shfl_sync(0xffffffffu, first, k); if (k < ncell && r >= fk) q = k; }
+        for (int k = 1; k < FOW_MAX_CELLS; ++k) { const int fk = __shfl_sync(0xffffffffu, first, k); if (k < ncell && r >= fk) q = k; }
         const int lo_q = __shfl_sync(0xffffffffu, seg.x, q), len_q = __shfl_sync(0xffffffffu, len, q);
         const int src_q = __shfl_sync(0xffffffffu, seg.z, q), has_q = __shfl_sync(0xffffffffu, seg.w, q);
         const int first_q = __shfl_sync(0xffffffffu, first, q);
@@ -668,9 +669,11 @@ static int fo_run(const srx_feature_args *a, const FoLayout &L, const int *fmap_
     const float one_minus = (float)(1.0 - (double)a->ratio);
     if (row_bytes <= 2048) {
         const int smem_w = FOW_WARPS * 2 * a->channels * 4;
-        const int per_cta = FOW_WARPS * FOW_CELLS;
+        int cpw = FOW_CELLS;
+        if (const char *e = getenv("SRX_FO_CELLS")) { cpw = atoi(e); cpw = cpw < 1 ? 1 : (cpw > FOW_MAX_CELLS ? FOW_MAX_CELLS : cpw); }
+        const int per_cta = FOW_WARPS * cpw;
         const int grid_w = a->batch * ((hw + per_cta - 1) / per_cta);
-#define FO_LAUNCH_WARP(P_) k_fo_style_warp<XT, P_><<<grid_w, FOW_WARPS * 32, smem_w, st>>>(feat, g, cellseg, uniq, mult, a->ratio, one_minus, stats, rows)
+#define FO_LAUNCH_WARP(P_) k_fo_style_warp<XT, P_><<<grid_w, FOW_WARPS * 32, smem_w, st>>>(feat, g, cellseg, uniq, mult, a->ratio, one_minus, cpw, stats, rows)
         const int nvec = row_bytes / 16;
         if (nvec <= 32) FO_LAUNCH_WARP(1);
         else if (nvec <= 64) FO_LAUNCH_WARP(2);
