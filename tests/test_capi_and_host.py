@@ -55,6 +55,16 @@ def test_no_cpu_fallback():
         OverlapPlan(ids, (1, 4, 1, 1))
     with pytest.raises(_lib.SrxUnavailable):
         OverlapCorresponder().step_finished(EngineData(IDMap(tensor=ids)), Ctx(torch.zeros(1, 4, 1, 1), 900))
+    # the round-2 entry points refuse CPU tensors the same way
+    from stable_renderer_b200.feature import feature_overlap, taichi_cells_overlap
+    from stable_renderer_b200.loaders import CreateNoiseSequenceFromIdMap
+    from stable_renderer_b200.overlap.johnny import overlap as johnny_overlap  # noqa: F401  (imports without a GPU)
+    with pytest.raises(_lib.SrxUnavailable):
+        feature_overlap(torch.zeros(1, 4, 16), IDMap(tensor=ids))
+    with pytest.raises(_lib.SrxUnavailable):
+        taichi_cells_overlap(torch.zeros(1, 64, 4), torch.zeros(1, 4, 8), torch.zeros(1, 4, 8), torch.zeros(1, 64))
+    with pytest.raises(_lib.SrxUnavailable):
+        CreateNoiseSequenceFromIdMap()(IDMap(tensor=torch.ones(1, 64, 64, 4, dtype=torch.int32)), 1)
 
 
 def test_argument_validation_without_gpu(lib):
