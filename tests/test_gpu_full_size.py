@@ -67,6 +67,17 @@ def test_full_size_step_properties(cfg):
     plan.step(s, 0.5)
     assert_close(t2n(s), t2n(x) * 2, 2e-5, 1e-5, cfg + " scaling")
 
+    # (7) without AdaIN the step is linear in the latents: (1 - r) x + r * mean_key(x)
+    x1 = x0.clone()
+    x2 = torch.roll(x0, 7, 0).contiguous() * 0.5
+    x12 = (x1 + x2).contiguous()
+    plan.step(x1, 0.5, adain=False)
+    plan.step(x2, 0.5, adain=False)
+    plan.step(x12, 0.5, adain=False)
+    plan.check()
+    assert_close(t2n(x12), t2n(x1 + x2), 2e-5, 1e-5, cfg + " linearity")
+    assert (x1 - x0).abs().max() > 0.1                                   # the step did something
+
 
 def test_full_size_step_bf16_cfg3():
     """config 3's dtype: bf16 latents, tolerance 1e-2 (north_star)."""
