@@ -526,25 +526,32 @@ def run_overlap(args, workload: str, rank: int, local: int, world: int, light: b
         ctx2 = _Ctx()
         ctx2.noise, ctx2.timestep, ctx2.total_steps = x_dev, 900, job_steps
 
+        ev_run = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
         def e2e_job_run(j: int):
+            ev_run[0].record()
             ids_dev.copy_(ids_host[j % n_rot], non_blocking=True)
+            ev_run[1].record()
             idm2.invalidate()
             for s in range(job_steps):
                 ctx2.step_index = s
                 x_dev.copy_(x_host, non_blocking=True)
                 oc2.step_finished(ed2, ctx2)
                 x_out.copy_(x_dev, non_blocking=True)
+            ev_run[2].record()
 
         for j in range(2):
             e2e_job_run(j)
         torch.cuda.synchronize()
-        run_ms = []
+        run_ms, ids_ms, steps_ms = [], [], []
         for j in range(n_runs):
             barrier(world)
             t_wall = time.perf_counter()
             e2e_job_run(j)
             torch.cuda.synchronize()
             run_ms.append((time.perf_counter() - t_wall) * 1e3)
+            ids_ms.append(ev_run[0].elapsed_time(ev_run[1]))
+            steps_ms.append(ev_run[1].elapsed_time(ev_run[2]))
         if world > 1:
             tr = torch.tensor(run_ms, dtype=torch.float64, device=dev)
             dist.all_reduce(tr, op=dist.ReduceOp.MAX)
@@ -554,6 +561,7 @@ def run_overlap(args, workload: str, rank: int, local: int, world: int, light: b
                    "steps_per_sec": job_steps * 1e3 / job_ms, "ms_per_step": job_ms / job_steps, "ms_per_run": job_ms,
                    "ms_per_run_p90": percentile(run_ms, 0.9), "ms_per_run_mean": statistics.mean(run_ms),
                    "ms_per_run_min": min(run_ms), "runs": n_runs, "steps": job_steps * n_runs,
+                   "ms_ids_h2d_per_run_rank0": statistics.median(ids_ms), "ms_steps_per_run_rank0": statistics.median(steps_ms),
                    "h2d_bytes_per_step": id_bytes // job_steps + x.numel() * elem, "d2h_bytes_per_step": x.numel() * elem,
                    "api": "OverlapCorresponder.step_finished(engine_data, sampling_context)",
                    "regime": f"runs of {job_steps} denoise steps on one id batch: ids H2D once per run ({id_bytes >> 20} MiB, "
